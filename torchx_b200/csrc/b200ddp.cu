@@ -1,0 +1,1167 @@
+// b200ddp.cu — libb200ddp.so: B200 (sm_100a) data plane for the `local_cuda` TorchX scheduler.
+//
+// What lives here (see include/b200ddp.h for the ABI and DESIGN.md for the rationale):
+//   * rendezvous: POSIX-shm control block + CUDA-IPC exchange of ONE symmetric arena per rank
+//     (replaces c10d TCPStore + ncclCommInitRank on the reference path,
+//      torchx/distributed/__init__.py:217-222 -> torch.distributed.init_process_group)
+//   * the DDP gradient-bucket allreduce as ONE fused kernel per bucket
+//     (replaces the 4-launch cast -> div -> ncclAllReduce -> copy sequence of
+//      torch/distributed/algorithms/ddp_comm_hooks/default_hooks.py:57-93)
+//       - one-shot  : push compressed message to every peer, one flag barrier, reduce locally
+//       - two-shot  : push-scatter (fp32->wire cast + scale fused into the NVLink stores)
+//                     -> reduce own slice (fp32 accumulate, rank order) -> pull-gather
+//                     (wire->fp32 cast fused into the NVLink loads)
+//   * broadcast / barrier on the same fabric (DDP init + BN-buffer sync, dist.barrier()).
+//
+// Memory model: every cross-GPU hand-off is  data stores -> bar.sync -> st.release.sys(flag)
+// on the producer and  ld.acquire.sys(flag) -> bar.sync -> data loads  on the consumer, with a
+// monotonically increasing sequence number instead of flag resets (no ABA, no reset races).
+// All peer waits are bounded: a CTA that waits longer than `timeout_ns` records B2_ETIMEOUT in a
+// host-mapped status word and carries on, so a dead peer can never hang the GPU.
+//
+// No tensor cores: the path is a pure bandwidth-bound reduction (1 add per 2-4 bytes moved).
+
+#include "../../include/b200ddp.h"
+
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <new>
+#include <string>
+
+// ------------------------------------------------------------------------------------------------
+// constants shared by host and device
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kThreads = 512;                // threads per CTA for every kernel in this file
+constexpr int kMaxCtas = 296;                // 2 x 148 SMs: upper bound on the grid of a collective
+constexpr int kFlagSlotBytes = 32;           // one 32 B sector of flags per CTA index (8 x u32, one per peer)
+constexpr size_t kFlagRegionBytes = 64 << 10;  // >= kMaxCtas * kFlagSlotBytes, keeps stages 64 KiB aligned
+constexpr size_t kDefaultStageBytes = 128ull << 20;
+constexpr unsigned long long kDefaultTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
+
+static_assert(kMaxCtas * kFlagSlotBytes <= (int)kFlagRegionBytes, "flag region too small");
+
+// Device-visible description of one rank's view of the communicator; passed BY VALUE as a kernel
+// parameter (well under the 4 KiB parameter limit), so no device-side indirection is needed.
+struct CommDev {
+  int rank;
+  int world;
+  uint8_t* peer[B2_MAX_WORLD];      // peer[jj] = symmetric arena of rank (rank + jj) % world as mapped in
+                                    // THIS process (peer[0] is this rank's own).  Pre-rotated on the host so
+                                    // unrolled device loops index it with compile-time constants (registers,
+                                    // not a local-memory copy of the parameter block) and so the W ranks
+                                    // never all target the same peer in the same loop step.
+  uint32_t* opseq;                  // local: number of collectives completed on this communicator
+  uint32_t* done;                   // local: CTAs of the running collective that reached the epilogue
+  uint32_t* status;                 // host-mapped: 0 = healthy, else a B2_E* code (positive)
+  unsigned long long timeout_ns;    // bound on any single peer wait
+  unsigned long long stage_off[2];  // byte offsets of the two staging buffers inside an arena
+  unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
+                                    //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced"
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+namespace dev {
+
+struct F8 {
+  float v[8];
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// 256-bit / 128-bit streaming accesses (LDG.E.NA.256 / STG.E.NA.256 on sm_100a).
+__device__ __forceinline__ F8 ldg_f8(const float* p) {
+  F8 r;
+  asm volatile("ld.global.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]),
+                 "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_f8(float* p, const F8& r) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p),
+               "f"(r.v[0]), "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]),
+               "f"(r.v[6]), "f"(r.v[7])
+               : "memory");
+}
+__device__ __forceinline__ uint4 ldg_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void stg_u4(void* p, const uint4& r) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y),
+               "r"(r.z), "r"(r.w)
+               : "memory");
+}
+
+// fp32 pair -> packed bf16x2 with round-to-nearest-even (one F2FP.BF16.F32.PACK_AB). `lo` lands
+// in bits [15:0] (the lower address in little-endian memory), `hi` in bits [31:16].
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float bf16_lo(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+
+// ---- per-mode traits ---------------------------------------------------------------------------
+// A "vec" is 8 consecutive elements everywhere in this file.
+template <int MODE>
+struct Wire;  // wire representation of one vec
+
+template <>
+struct Wire<B2_F32_WIRE_BF16> {
+  static constexpr int kBytes = 16;
+  uint4 q;
+};
+template <>
+struct Wire<B2_BF16> {
+  static constexpr int kBytes = 16;
+  uint4 q;
+};
+template <>
+struct Wire<B2_F32> {
+  static constexpr int kBytes = 32;
+  F8 f;
+};
+
+template <int MODE>
+__device__ __forceinline__ Wire<MODE> ld_wire(const uint8_t* p) {
+  Wire<MODE> w;
+  if constexpr (MODE == B2_F32) {
+    w.f = ldg_f8(reinterpret_cast<const float*>(p));
+  } else {
+    w.q = ldg_u4(p);
+  }
+  return w;
+}
+template <int MODE>
+__device__ __forceinline__ void st_wire(uint8_t* p, const Wire<MODE>& w) {
+  if constexpr (MODE == B2_F32) {
+    stg_f8(reinterpret_cast<float*>(p), w.f);
+  } else {
+    stg_u4(p, w.q);
+  }
+}
+
+// wire(scale * x): the value a rank contributes.  Rounding points are part of the contract
+// (oracle/allreduce_oracle.c: b2o_compress):
+//   F32_WIRE_BF16 : bf16( float(bf16(x)) * scale )      == `buf.to(bf16).div_(W)` for W = 2^k
+//   BF16          : bf16( float(x) * scale )            (x is already bf16)
+//   F32           : x * scale                           == Reducer's `mul_out(bucket, grad, 1/W)`
+template <int MODE>
+__device__ __forceinline__ Wire<MODE> compress(const F8& x, float scale) {
+  Wire<MODE> w;
+  if constexpr (MODE == B2_F32) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w.f.v[i] = __fmul_rn(x.v[i], scale);
+  } else {
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = x.v[2 * i], b = x.v[2 * i + 1];
+      if constexpr (MODE == B2_F32_WIRE_BF16) {
+        const uint32_t p = pack_bf16x2(a, b);  // first rounding: the `.to(bf16)` cast
+        a = bf16_lo(p);
+        b = bf16_hi(p);
+      }
+      o[i] = pack_bf16x2(__fmul_rn(a, scale), __fmul_rn(b, scale));
+    }
+    w.q = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+  return w;
+}
+
+template <int MODE>
+__device__ __forceinline__ F8 widen(const Wire<MODE>& w) {
+  if constexpr (MODE == B2_F32) {
+    return w.f;
+  } else {
+    F8 r;
+    r.v[0] = bf16_lo(w.q.x);
+    r.v[1] = bf16_hi(w.q.x);
+    r.v[2] = bf16_lo(w.q.y);
+    r.v[3] = bf16_hi(w.q.y);
+    r.v[4] = bf16_lo(w.q.z);
+    r.v[5] = bf16_hi(w.q.z);
+    r.v[6] = bf16_lo(w.q.w);
+    r.v[7] = bf16_hi(w.q.w);
+    return r;
+  }
+}
+
+// round(s): the reduced value as it travels in the gather phase / is stored.
+template <int MODE>
+__device__ __forceinline__ Wire<MODE> finalize(const F8& s) {
+  Wire<MODE> w;
+  if constexpr (MODE == B2_F32) {
+    w.f = s;
+  } else {
+    w.q = make_uint4(pack_bf16x2(s.v[0], s.v[1]), pack_bf16x2(s.v[2], s.v[3]),
+                     pack_bf16x2(s.v[4], s.v[5]), pack_bf16x2(s.v[6], s.v[7]));
+  }
+  return w;
+}
+
+__device__ __forceinline__ void accumulate(F8& s, const F8& c) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s.v[i] = __fadd_rn(s.v[i], c.v[i]);
+}
+
+// ---- local bucket accesses (the caller's tensor: any alignment, any length) --------------------
+template <int MODE>
+__device__ __forceinline__ F8 load_in(const void* buf, unsigned long long e, unsigned long long n,
+                                      bool aligned) {
+  F8 x;
+  if constexpr (MODE == B2_BF16) {
+    const uint16_t* p = reinterpret_cast<const uint16_t*>(buf) + e;
+    if (aligned && e + 8 <= n) {
+      Wire<B2_BF16> w;
+      w.q = ldg_u4(p);
+      x = widen<B2_BF16>(w);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        x.v[i] = (e + i < n) ? __uint_as_float(static_cast<uint32_t>(p[i]) << 16) : 0.f;
+    }
+  } else {
+    const float* p = reinterpret_cast<const float*>(buf) + e;
+    if (aligned && e + 8 <= n) {
+      x = ldg_f8(p);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x.v[i] = (e + i < n) ? p[i] : 0.f;
+    }
+  }
+  return x;
+}
+
+// `w` is the reduced vec in wire format; writes it to the caller's tensor in the tensor's dtype.
+template <int MODE>
+__device__ __forceinline__ void store_out(void* buf, unsigned long long e, unsigned long long n,
+                                          bool aligned, const Wire<MODE>& w) {
+  if constexpr (MODE == B2_BF16) {
+    uint16_t* p = reinterpret_cast<uint16_t*>(buf) + e;
+    if (aligned && e + 8 <= n) {
+      stg_u4(p, w.q);
+    } else {
+      const uint32_t q[4] = {w.q.x, w.q.y, w.q.z, w.q.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (e + i < n) p[i] = static_cast<uint16_t>((q[i >> 1] >> ((i & 1) * 16)) & 0xffffu);
+    }
+  } else {
+    float* p = reinterpret_cast<float*>(buf) + e;
+    const F8 r = widen<MODE>(w);
+    if (aligned && e + 8 <= n) {
+      stg_f8(p, r);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (e + i < n) p[i] = r.v[i];
+    }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ bool buf_aligned(const void* buf) {
+  return (reinterpret_cast<uintptr_t>(buf) & (MODE == B2_BF16 ? 15u : 31u)) == 0;
+}
+
+// ---- cross-GPU barrier among the CTAs with the same blockIdx.x on every rank --------------------
+// Thread p (< world) publishes `seq` into peer p's flag slot for this CTA index and waits for peer
+// p's `seq` in its own slot.  Sequence numbers only grow, so "flag >= seq" (wrap-safe) is the test.
+__device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
+  __syncthreads();  // all of this CTA's data stores are ordered before the release below
+  if (threadIdx.x < c.world) {
+    const int jj = threadIdx.x;  // this thread pairs with rank p = (rank + jj) % world
+    int p = c.rank + jj;
+    if (p >= c.world) p -= c.world;
+    uint8_t* their_arena = c.peer[0];
+#pragma unroll
+    for (int i = 1; i < B2_MAX_WORLD; ++i)
+      if (jj == i) their_arena = c.peer[i];  // select chain: keeps the parameter block out of local memory
+    const size_t slot = static_cast<size_t>(blockIdx.x) * kFlagSlotBytes;
+    uint32_t* theirs = reinterpret_cast<uint32_t*>(their_arena + slot) + c.rank;
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[0] + slot) + p;
+    st_release_sys(theirs, seq);
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - seq) < 0) {
+      if ((++spins & 63u) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) {
+          t0 = now;
+        } else if (now - t0 > c.timeout_ns) {
+          *reinterpret_cast<volatile uint32_t*>(c.status) = static_cast<uint32_t>(-B2_ETIMEOUT);
+          __threadfence_system();
+          break;  // give up: results are undefined, but the GPU is not hung
+        }
+      }
+    }
+  }
+  __syncthreads();  // peers' data is now visible to every thread of this CTA
+}
+
+// Every collective kernel starts by reading the communicator's op counter (parity selects the
+// staging buffer, the value seeds this op's flag sequence numbers) and ends by bumping it once
+// all CTAs are through.  Keeping the counter on the device makes the launch sequence CUDA-graph
+// replayable and keeps the host stateless.
+__device__ __forceinline__ uint32_t op_begin(const CommDev& c) { return ld_volatile_u32(c.opseq); }
+
+__device__ __forceinline__ void op_end(const CommDev& c, uint32_t seq0) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(c.done, 1u) == gridDim.x - 1) {
+      *reinterpret_cast<volatile uint32_t*>(c.done) = 0;
+      __threadfence();
+      *reinterpret_cast<volatile uint32_t*>(c.opseq) = seq0 + 1;
+    }
+  }
+}
+
+template <int W>
+struct Unroll {  // vecs per thread per loop trip, chosen so ~8 wire vecs are in flight per thread
+  static constexpr int kU = (W >= 8) ? 1 : (W >= 4 ? 2 : (W >= 2 ? 4 : 8));
+};
+
+}  // namespace dev
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+// W == 1 (and the single-GPU roofline probe): x <- round(wire(scale * x)), one streaming pass.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) k_local_pass(void* buf, unsigned long long n, float scale) {
+  using namespace dev;
+  const bool aligned = buf_aligned<MODE>(buf);
+  const unsigned long long V = (n + 7) / 8;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  constexpr int U = 4;
+  for (unsigned long long v0 = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+       v0 < V; v0 += stride * U) {
+    F8 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) x[u] = load_in<MODE>(buf, v * 8, n, aligned);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) {
+        const Wire<MODE> c = compress<MODE>(x[u], scale);
+        store_out<MODE>(buf, v * 8, n, aligned, finalize<MODE>(widen<MODE>(c)));
+      }
+    }
+  }
+}
+
+// One-shot: latency regime.  Wire traffic per rank: (W-1) * S out, (W-1) * S in.
+template <int MODE, int W>
+__global__ void __launch_bounds__(kThreads, 1)
+    k_oneshot(CommDev c, void* buf, unsigned long long n, float scale) {
+  using namespace dev;
+  constexpr int WVB = Wire<MODE>::kBytes;
+  constexpr int U = Unroll<W>::kU;
+  const uint32_t seq0 = op_begin(c);
+  const unsigned long long stage = (seq0 & 1u) ? c.stage_off[1] : c.stage_off[0];
+  const bool aligned = buf_aligned<MODE>(buf);
+  const unsigned long long V = (n + 7) / 8;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+
+  // phase A: compress my message once, push it into recv[rank] of every rank (mine included)
+  for (unsigned long long v0 = first; v0 < V; v0 += stride * U) {
+    F8 x[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) x[u] = load_in<MODE>(buf, v * 8, n, aligned);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) {
+        const Wire<MODE> w = compress<MODE>(x[u], scale);
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj)  // peer[] is rotated: the W ranks never hammer one peer at a time
+          st_wire<MODE>(c.peer[jj] + stage + c.rank * c.slice_cap + v * WVB, w);
+      }
+    }
+  }
+  cta_xbar(c, seq0 * 4u + 1u);
+
+  // phase B: reduce the W messages (all local now) in rank order, write the caller's tensor
+  const uint8_t* mine = c.peer[0] + stage;
+  for (unsigned long long v0 = first; v0 < V; v0 += stride * U) {
+    Wire<MODE> w[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) {
+#pragma unroll
+        for (int r = 0; r < W; ++r) w[u][r] = ld_wire<MODE>(mine + r * c.slice_cap + v * WVB);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+      if (v < V) {
+        F8 s = widen<MODE>(w[u][0]);
+#pragma unroll
+        for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));
+        store_out<MODE>(buf, v * 8, n, aligned, finalize<MODE>(s));
+      }
+    }
+  }
+  op_end(c, seq0);
+}
+
+// Two-shot: bandwidth regime.  The message is cut into W slices of Ls vecs; rank i owns slice i.
+//   A  push-scatter : read my fp32 bucket once, cast+scale, STORE slice j into rank j's recv[me]
+//   B  reduce       : sum recv[0..W-1] of my slice (local HBM), fp32 accumulate in rank order,
+//                     round once, write my "reduced" region
+//   C  pull-gather  : LOAD slice j from rank j's "reduced" region over NVLink, widen, write bucket
+// Wire traffic per rank and direction: 2 * (W-1)/W * S  (the allreduce lower bound for P2P).
+// CTA b touches the same vec indices of a slice on every rank and in every phase, so the only
+// synchronisation needed is among the CTAs with equal blockIdx.x across ranks (no grid sync).
+template <int MODE, int W>
+__global__ void __launch_bounds__(kThreads, 1)
+    k_twoshot(CommDev c, void* buf, unsigned long long n, float scale) {
+  using namespace dev;
+  constexpr int WVB = Wire<MODE>::kBytes;
+  constexpr int U = Unroll<W>::kU;
+  const uint32_t seq0 = op_begin(c);
+  const unsigned long long stage = (seq0 & 1u) ? c.stage_off[1] : c.stage_off[0];
+  const bool aligned = buf_aligned<MODE>(buf);
+  const unsigned long long V = (n + 7) / 8;
+  const unsigned long long Ls = (V + W - 1) / W;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const unsigned long long my_recv = stage + c.rank * c.slice_cap;
+  const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;
+
+  // ---- phase A -------------------------------------------------------------------------------
+  for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+    F8 x[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) x[u][jj] = load_in<MODE>(buf, gv * 8, n, aligned);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V)
+          st_wire<MODE>(c.peer[jj] + my_recv + v * WVB, compress<MODE>(x[u][jj], scale));
+      }
+    }
+  }
+  cta_xbar(c, seq0 * 4u + 1u);
+
+  // ---- phase B -------------------------------------------------------------------------------
+  {
+    uint8_t* mine = c.peer[0];
+    const unsigned long long base = c.rank * Ls;
+    for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+      Wire<MODE> w[U][W];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long v = v0 + u * stride;
+        if (v < Ls && base + v < V) {
+#pragma unroll
+          for (int r = 0; r < W; ++r)
+            w[u][r] = ld_wire<MODE>(mine + stage + r * c.slice_cap + v * WVB);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long v = v0 + u * stride;
+        if (v < Ls && base + v < V) {
+          F8 s = widen<MODE>(w[u][0]);
+#pragma unroll
+          for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));
+          st_wire<MODE>(mine + reduced + v * WVB, finalize<MODE>(s));
+        }
+      }
+    }
+  }
+  cta_xbar(c, seq0 * 4u + 2u);
+
+  // ---- phase C -------------------------------------------------------------------------------
+  for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+    Wire<MODE> w[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) w[u][jj] = ld_wire<MODE>(c.peer[jj] + reduced + v * WVB);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
+      }
+    }
+  }
+  op_end(c, seq0);
+}
+
+// Broadcast of raw bytes: root pushes into every peer's stage, one barrier, peers copy out.
+__global__ void __launch_bounds__(kThreads, 1)
+    k_broadcast(CommDev c, uint8_t* buf, unsigned long long bytes, int root) {
+  using namespace dev;
+  const uint32_t seq0 = op_begin(c);
+  const unsigned long long stage = (seq0 & 1u) ? c.stage_off[1] : c.stage_off[0];
+  const bool aligned = (reinterpret_cast<uintptr_t>(buf) & 15u) == 0;
+  const unsigned long long nvec = aligned ? bytes / 16 : 0;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  if (c.rank == root) {
+    for (unsigned long long v = first; v < nvec; v += stride) {
+      const uint4 q = ldg_u4(buf + v * 16);
+#pragma unroll
+      for (int jj = 1; jj < B2_MAX_WORLD; ++jj)
+        if (jj < c.world) stg_u4(c.peer[jj] + stage + v * 16, q);
+    }
+    for (unsigned long long b = nvec * 16 + first; b < bytes; b += stride) {
+      const uint8_t x = buf[b];
+#pragma unroll
+      for (int jj = 1; jj < B2_MAX_WORLD; ++jj)
+        if (jj < c.world) c.peer[jj][stage + b] = x;
+    }
+  }
+  cta_xbar(c, seq0 * 4u + 1u);
+  if (c.rank != root) {
+    const uint8_t* src = c.peer[0] + stage;
+    for (unsigned long long v = first; v < nvec; v += stride) stg_u4(buf + v * 16, ldg_u4(src + v * 16));
+    for (unsigned long long b = nvec * 16 + first; b < bytes; b += stride) buf[b] = src[b];
+  }
+  op_end(c, seq0);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_barrier(CommDev c) {
+  using namespace dev;
+  const uint32_t seq0 = op_begin(c);
+  cta_xbar(c, seq0 * 4u + 1u);
+  op_end(c, seq0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char tmp[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(tmp, sizeof(tmp), fmt, ap);
+  va_end(ap);
+  g_err = tmp;
+  return code;
+}
+
+#define B2_CUDA(expr)                                                                         \
+  do {                                                                                        \
+    cudaError_t e__ = (expr);                                                                 \
+    if (e__ != cudaSuccess)                                                                   \
+      return fail(B2_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                  __LINE__);                                                                  \
+  } while (0)
+
+struct DeviceGuard {  // the library never leaves the caller's current device changed
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+double now_s() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+// ---- shm control block (multi-process rendezvous) ----------------------------------------------
+constexpr uint64_t kShmMagic = 0x42323030444450ull;  // "B200DDP"
+
+struct ShmSlot {
+  cudaIpcMemHandle_t handle;
+  int device;
+  int pid;
+  unsigned long long arena_bytes;
+  std::atomic<uint32_t> ready;  // 1 once handle/device/pid are valid
+  char pad[64];
+};
+
+struct ShmBlock {
+  std::atomic<uint64_t> magic;
+  uint64_t epoch;
+  int world;
+  std::atomic<int> mapped;    // ranks that have opened every peer handle
+  std::atomic<int> departed;  // ranks that have finished using peer memory (destroy handshake)
+  ShmSlot slot[B2_MAX_WORLD];
+};
+
+}  // namespace
+
+struct b2_comm {
+  CommDev d{};
+  int device = -1;
+  bool local_world = false;    // created by b2_comm_create_local (no IPC, no shm)
+  bool peer_is_ipc[B2_MAX_WORLD] = {};
+  uint8_t* arena_of[B2_MAX_WORLD] = {};  // arena_of[r] = rank r's arena as mapped in this process
+  void* arena = nullptr;       // cudaMalloc'ed: [flags | stage0 | stage1]
+  size_t arena_bytes = 0;
+  size_t stage_bytes = 0;
+  uint32_t* counters = nullptr;  // cudaMalloc'ed: opseq, done
+  uint32_t* status_host = nullptr;
+  int max_ctas = 0;              // 0 = heuristic
+  size_t oneshot_max_wire_bytes = 256 << 10;
+  uint64_t launches = 0;
+  ShmBlock* shm = nullptr;
+  std::string shm_path;
+};
+
+namespace {
+
+size_t env_size(const char* name, size_t dflt) {
+  const char* s = getenv(name);
+  if (!s || !*s) return dflt;
+  char* end = nullptr;
+  unsigned long long v = strtoull(s, &end, 10);
+  return end == s ? dflt : static_cast<size_t>(v);
+}
+
+// Arena layout for a given world size; fills d.stage_off / d.slice_cap.
+void layout(b2_comm* c, int world, size_t stage_bytes) {
+  size_t cap = stage_bytes / (world + 1);
+  cap &= ~static_cast<size_t>(255);
+  c->stage_bytes = cap * (world + 1);
+  c->d.slice_cap = cap;
+  c->d.stage_off[0] = kFlagRegionBytes;
+  c->d.stage_off[1] = kFlagRegionBytes + c->stage_bytes;
+  c->arena_bytes = kFlagRegionBytes + 2 * c->stage_bytes;
+}
+
+int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
+  c->device = device;
+  c->d.rank = rank;
+  c->d.world = world;
+  if (stage_bytes == 0) stage_bytes = env_size("B2_STAGE_MB", kDefaultStageBytes >> 20) << 20;
+  if (stage_bytes < (static_cast<size_t>(world + 1) << 12))
+    return fail(B2_EINVAL, "stage_bytes=%zu too small for world=%d", stage_bytes, world);
+  layout(c, world, stage_bytes);
+  c->d.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
+  c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
+  c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", c->oneshot_max_wire_bytes);
+  B2_CUDA(cudaSetDevice(device));
+  B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
+  B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
+  B2_CUDA(cudaMalloc(&c->counters, 256));
+  B2_CUDA(cudaMemset(c->counters, 0, 256));
+  c->d.opseq = c->counters;
+  c->d.done = c->counters + 32;  // a different 128 B line
+  B2_CUDA(cudaHostAlloc(&c->status_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  memset(c->status_host, 0, 64);
+  void* sdev = nullptr;
+  B2_CUDA(cudaHostGetDevicePointer(&sdev, c->status_host, 0));
+  c->d.status = static_cast<uint32_t*>(sdev);
+  B2_CUDA(cudaDeviceSynchronize());
+  c->arena_of[rank] = static_cast<uint8_t*>(c->arena);
+  return B2_OK;
+}
+
+void rotate_peers(b2_comm* c) {
+  for (int jj = 0; jj < c->d.world; ++jj) c->d.peer[jj] = c->arena_of[(c->d.rank + jj) % c->d.world];
+}
+
+void free_rank_resources(b2_comm* c) {
+  if (c->device >= 0) cudaSetDevice(c->device);
+  if (c->arena) cudaFree(c->arena);
+  if (c->counters) cudaFree(c->counters);
+  if (c->status_host) cudaFreeHost(c->status_host);
+  c->arena = nullptr;
+  c->counters = nullptr;
+  c->status_host = nullptr;
+}
+
+int grid_for(const b2_comm* c, unsigned long long vecs_per_cta_dim, int unroll) {
+  // Enough CTAs that each thread has work, capped so the collective leaves SMs to the backward
+  // pass it overlaps with.  Deterministic in (n, world, max_ctas) => identical on every rank.
+  const int cap = c->max_ctas > 0 ? (c->max_ctas > kMaxCtas ? kMaxCtas : c->max_ctas) : 64;
+  unsigned long long per = static_cast<unsigned long long>(kThreads) * unroll;
+  unsigned long long g = (vecs_per_cta_dim + per - 1) / per;
+  if (g < 1) g = 1;
+  if (g > static_cast<unsigned long long>(cap)) g = cap;
+  return static_cast<int>(g);
+}
+
+template <int W>
+constexpr int unroll_of() {
+  return dev::Unroll<W>::kU;
+}
+
+int unroll_for_world(int w) { return w >= 8 ? 1 : (w >= 4 ? 2 : (w >= 2 ? 4 : 8)); }
+
+template <int MODE, int W>
+cudaError_t launch_oneshot(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+                           cudaStream_t s) {
+  k_oneshot<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  return cudaGetLastError();
+}
+template <int MODE, int W>
+cudaError_t launch_twoshot(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+                           cudaStream_t s) {
+  k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_by_world(const b2_comm* c, bool oneshot, int grid, void* buf, unsigned long long n,
+                            float scale, cudaStream_t s) {
+#define B2_CASE(Wv)                                                                    \
+  case Wv:                                                                             \
+    return oneshot ? launch_oneshot<MODE, Wv>(c, grid, buf, n, scale, s)               \
+                   : launch_twoshot<MODE, Wv>(c, grid, buf, n, scale, s);
+  switch (c->d.world) {
+    B2_CASE(2)
+    B2_CASE(3)
+    B2_CASE(4)
+    B2_CASE(5)
+    B2_CASE(6)
+    B2_CASE(7)
+    B2_CASE(8)
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef B2_CASE
+}
+
+template <int MODE>
+cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStream_t s) {
+  const unsigned long long V = (n + 7) / 8;
+  unsigned long long g = (V + kThreads * 4ull - 1) / (kThreads * 4ull);
+  if (g < 1) g = 1;
+  if (g > 148ull * 4) g = 148ull * 4;  // 4 resident CTAs per SM keep ~64 KiB of loads in flight per SM
+  k_local_pass<MODE><<<static_cast<int>(g), kThreads, 0, s>>>(buf, n, scale);
+  return cudaGetLastError();
+}
+
+size_t elem_bytes(int mode) { return mode == B2_BF16 ? 2 : 4; }
+size_t wire_vec_bytes(int mode) { return mode == B2_F32 ? 32 : 16; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int b2_version(void) { return B2_ABI_VERSION; }
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+int b2_comm_create_local(b2_comm_t** out, int world, const int* devices, size_t stage_bytes) {
+  if (!out || !devices || world < 1 || world > B2_MAX_WORLD)
+    return fail(B2_EINVAL, "b2_comm_create_local: bad arguments (world=%d)", world);
+  int prev = -1;
+  cudaGetDevice(&prev);
+  b2_comm* cs[B2_MAX_WORLD] = {};
+  int rc = B2_OK;
+  for (int r = 0; r < world && rc == B2_OK; ++r) {
+    cs[r] = new (std::nothrow) b2_comm();
+    if (!cs[r]) {
+      rc = fail(B2_ESYS, "out of host memory");
+      break;
+    }
+    cs[r]->local_world = true;
+    rc = alloc_rank_resources(cs[r], r, world, devices[r], stage_bytes);
+  }
+  for (int a = 0; a < world && rc == B2_OK; ++a) {
+    for (int b = 0; b < world && rc == B2_OK; ++b) {
+      if (devices[a] == devices[b]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+      if (!can) {
+        rc = fail(B2_ENOPEER, "device %d cannot access device %d over P2P", devices[a], devices[b]);
+        break;
+      }
+      cudaSetDevice(devices[a]);
+      cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+      } else if (e != cudaSuccess) {
+        rc = fail(B2_ECUDA, "cudaDeviceEnablePeerAccess(%d->%d): %s", devices[a], devices[b],
+                  cudaGetErrorString(e));
+      }
+    }
+  }
+  if (rc == B2_OK) {
+    for (int a = 0; a < world; ++a)
+      for (int b = 0; b < world; ++b) cs[a]->arena_of[b] = static_cast<uint8_t*>(cs[b]->arena);
+    for (int r = 0; r < world; ++r) {
+      rotate_peers(cs[r]);
+      out[r] = cs[r];
+    }
+  } else {
+    for (int r = 0; r < world; ++r)
+      if (cs[r]) {
+        free_rank_resources(cs[r]);
+        delete cs[r];
+      }
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int b2_comm_create(b2_comm_t** out, int rank, int world, int device, const char* shm_name,
+                   uint64_t epoch, size_t stage_bytes, int timeout_ms) {
+  if (!out || world < 1 || world > B2_MAX_WORLD || rank < 0 || rank >= world || device < 0)
+    return fail(B2_EINVAL, "b2_comm_create: bad arguments (rank=%d world=%d device=%d)", rank, world,
+                device);
+  if (world > 1 && (!shm_name || !*shm_name))
+    return fail(B2_EINVAL, "b2_comm_create: shm_name is required when world > 1");
+  const double deadline = now_s() + (timeout_ms > 0 ? timeout_ms : 120000) * 1e-3;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  b2_comm* c = new (std::nothrow) b2_comm();
+  if (!c) return fail(B2_ESYS, "out of host memory");
+  int rc = alloc_rank_resources(c, rank, world, device, stage_bytes);
+  int fd = -1;
+  if (rc == B2_OK && world > 1) {
+    char path[256];
+    snprintf(path, sizeof(path), "%s%s.e%llu", shm_name[0] == '/' ? "" : "/", shm_name,
+             static_cast<unsigned long long>(epoch));
+    c->shm_path = path;
+    fd = shm_open(path, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) rc = fail(B2_ESYS, "shm_open(%s): %s", path, strerror(errno));
+    if (rc == B2_OK && ftruncate(fd, sizeof(ShmBlock)) != 0)
+      rc = fail(B2_ESYS, "ftruncate(%s): %s", path, strerror(errno));
+    if (rc == B2_OK) {
+      void* m = mmap(nullptr, sizeof(ShmBlock), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+      if (m == MAP_FAILED)
+        rc = fail(B2_ESYS, "mmap(%s): %s", path, strerror(errno));
+      else
+        c->shm = static_cast<ShmBlock*>(m);
+    }
+    if (fd >= 0) close(fd);
+  }
+  if (rc == B2_OK && world > 1) {
+    ShmBlock* sb = c->shm;
+    ShmSlot& me = sb->slot[rank];
+    cudaError_t e = cudaIpcGetMemHandle(&me.handle, c->arena);
+    if (e != cudaSuccess) rc = fail(B2_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    if (rc == B2_OK) {
+      me.device = device;
+      me.pid = static_cast<int>(getpid());
+      me.arena_bytes = c->arena_bytes;
+      if (rank == 0) {
+        sb->epoch = epoch;
+        sb->world = world;
+        sb->magic.store(kShmMagic, std::memory_order_release);
+      }
+      me.ready.store(1, std::memory_order_release);
+    }
+    // wait for every rank's slot
+    for (int r = 0; r < world && rc == B2_OK; ++r) {
+      while (sb->slot[r].ready.load(std::memory_order_acquire) != 1) {
+        if (now_s() > deadline) {
+          rc = fail(B2_ETIMEOUT, "rendezvous timed out waiting for rank %d on %s", r, c->shm_path.c_str());
+          break;
+        }
+        usleep(200);
+      }
+    }
+    // map every peer's arena
+    for (int r = 0; r < world && rc == B2_OK; ++r) {
+      if (r == rank) continue;
+      const ShmSlot& ps = sb->slot[r];
+      if (ps.arena_bytes != c->arena_bytes) {
+        rc = fail(B2_EINVAL, "rank %d uses arena_bytes=%llu, this rank %zu (stage size must match)", r,
+                  ps.arena_bytes, c->arena_bytes);
+        break;
+      }
+      if (ps.device != device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, device, ps.device);
+        if (!can) {
+          rc = fail(B2_ENOPEER, "device %d cannot access rank %d's device %d over P2P", device, r, ps.device);
+          break;
+        }
+      }
+      void* p = nullptr;
+      e = cudaIpcOpenMemHandle(&p, ps.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        rc = fail(B2_ECUDA, "cudaIpcOpenMemHandle(rank %d, device %d): %s", r, ps.device,
+                  cudaGetErrorString(e));
+        break;
+      }
+      c->arena_of[r] = static_cast<uint8_t*>(p);
+      c->peer_is_ipc[r] = true;
+    }
+    if (rc == B2_OK) {
+      sb->mapped.fetch_add(1, std::memory_order_acq_rel);
+      while (sb->mapped.load(std::memory_order_acquire) < world) {
+        if (now_s() > deadline) {
+          rc = fail(B2_ETIMEOUT, "rendezvous timed out waiting for peers to map (%d/%d)",
+                    sb->mapped.load(), world);
+          break;
+        }
+        usleep(200);
+      }
+    }
+    // everyone holds a mapping now: the name can go (the memory lives until the last munmap)
+    if (rc == B2_OK && rank == 0) shm_unlink(c->shm_path.c_str());
+  }
+  if (rc != B2_OK) {
+    std::string keep = g_err;
+    for (int r = 0; r < world; ++r)
+      if (c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->arena_of[r]);
+    if (c->shm) munmap(c->shm, sizeof(ShmBlock));
+    if (rank == 0 && !c->shm_path.empty()) shm_unlink(c->shm_path.c_str());
+    free_rank_resources(c);
+    delete c;
+    g_err = keep;
+  } else {
+    rotate_peers(c);
+    *out = c;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+int b2_comm_destroy(b2_comm_t* c) {
+  if (!c) return B2_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->shm) {
+    // nobody frees its arena while a peer may still have kernels reading it
+    ShmBlock* sb = c->shm;
+    sb->departed.fetch_add(1, std::memory_order_acq_rel);
+    const double deadline = now_s() + 10.0;
+    while (sb->departed.load(std::memory_order_acquire) < c->d.world && now_s() < deadline) usleep(200);
+    for (int r = 0; r < c->d.world; ++r)
+      if (c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->arena_of[r]);
+    munmap(c->shm, sizeof(ShmBlock));
+  }
+  free_rank_resources(c);
+  delete c;
+  if (prev >= 0) cudaSetDevice(prev);
+  return B2_OK;
+}
+
+int b2_comm_rank(const b2_comm_t* c) { return c ? c->d.rank : B2_EINVAL; }
+int b2_comm_world(const b2_comm_t* c) { return c ? c->d.world : B2_EINVAL; }
+int b2_comm_device(const b2_comm_t* c) { return c ? c->device : B2_EINVAL; }
+
+int b2_comm_set_timeout_ms(b2_comm_t* c, int timeout_ms) {
+  if (!c || timeout_ms <= 0) return fail(B2_EINVAL, "b2_comm_set_timeout_ms: bad arguments");
+  c->d.timeout_ns = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
+  return B2_OK;
+}
+
+int b2_comm_set_max_ctas(b2_comm_t* c, int max_ctas) {
+  if (!c || max_ctas < 0) return fail(B2_EINVAL, "b2_comm_set_max_ctas: bad arguments");
+  c->max_ctas = max_ctas;
+  return B2_OK;
+}
+
+int b2_comm_status(const b2_comm_t* c) {
+  if (!c) return fail(B2_EINVAL, "null communicator");
+  const uint32_t s = *reinterpret_cast<volatile uint32_t*>(c->status_host);
+  if (s == 0) return B2_OK;
+  return fail(-static_cast<int>(s), "rank %d: a kernel gave up waiting for a peer (code %d)", c->d.rank,
+              -static_cast<int>(s));
+}
+
+uint64_t b2_comm_launch_count(const b2_comm_t* c) { return c ? c->launches : 0; }
+
+int b2_local_pass(void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
+  if (n_elems == 0) return B2_OK;
+  if (!buf) return fail(B2_EINVAL, "b2_local_pass: null buffer");
+  DeviceGuard g(device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (mode) {
+    case B2_F32_WIRE_BF16:
+      e = launch_local<B2_F32_WIRE_BF16>(buf, n_elems, scale, s);
+      break;
+    case B2_F32:
+      e = launch_local<B2_F32>(buf, n_elems, scale, s);
+      break;
+    case B2_BF16:
+      e = launch_local<B2_BF16>(buf, n_elems, scale, s);
+      break;
+    default:
+      return fail(B2_EINVAL, "unknown mode %d", mode);
+  }
+  if (e != cudaSuccess) return fail(B2_ECUDA, "k_local_pass launch: %s", cudaGetErrorString(e));
+  return B2_OK;
+}
+
+int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
+  if (!c) return fail(B2_EINVAL, "null communicator");
+  if (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16)
+    return fail(B2_EINVAL, "unknown mode %d", mode);
+  if (algo != B2_ALGO_AUTO && algo != B2_ALGO_ONESHOT && algo != B2_ALGO_TWOSHOT)
+    return fail(B2_EINVAL, "unknown algo %d", algo);
+  if (n_elems == 0) return B2_OK;
+  if (!buf) return fail(B2_EINVAL, "b2_allreduce: null buffer");
+  if (*reinterpret_cast<volatile uint32_t*>(c->status_host) != 0)
+    return fail(B2_ESTATE, "communicator poisoned by an earlier peer-wait timeout");
+  const int W = c->d.world;
+  if (W == 1) {
+    if (mode == B2_F32 && scale == 1.0f) return B2_OK;  // identity
+    int rc = b2_local_pass(buf, n_elems, mode, scale, c->device, stream);
+    if (rc == B2_OK) c->launches++;
+    return rc;
+  }
+  DeviceGuard g(c->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t wvb = wire_vec_bytes(mode);
+  const size_t cap_vecs = c->d.slice_cap / wvb;  // vecs one region can hold
+  const int U = unroll_for_world(W);
+  uint8_t* p = static_cast<uint8_t*>(buf);
+  size_t left = n_elems;
+  while (left > 0) {
+    const unsigned long long V_left = (left + 7) / 8;
+    bool oneshot;
+    if (algo == B2_ALGO_ONESHOT) {
+      oneshot = true;
+    } else if (algo == B2_ALGO_TWOSHOT) {
+      oneshot = false;
+    } else {
+      oneshot = V_left * wvb <= c->oneshot_max_wire_bytes && V_left <= cap_vecs;
+    }
+    const unsigned long long max_vecs = oneshot ? cap_vecs : cap_vecs * W;
+    const unsigned long long V = V_left < max_vecs ? V_left : max_vecs;
+    const size_t n = V == V_left ? left : static_cast<size_t>(V) * 8;
+    const unsigned long long per_cta_dim = oneshot ? V : (V + W - 1) / W;
+    const int grid = grid_for(c, per_cta_dim, U);
+    cudaError_t e;
+    switch (mode) {
+      case B2_F32_WIRE_BF16:
+        e = launch_by_world<B2_F32_WIRE_BF16>(c, oneshot, grid, p, n, scale, s);
+        break;
+      case B2_F32:
+        e = launch_by_world<B2_F32>(c, oneshot, grid, p, n, scale, s);
+        break;
+      default:
+        e = launch_by_world<B2_BF16>(c, oneshot, grid, p, n, scale, s);
+        break;
+    }
+    if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
+    c->launches++;
+    p += n * elem_bytes(mode);
+    left -= n;
+  }
+  return B2_OK;
+}
+
+int b2_broadcast(b2_comm_t* c, void* buf, size_t bytes, int root, void* stream) {
+  if (!c) return fail(B2_EINVAL, "null communicator");
+  if (root < 0 || root >= c->d.world) return fail(B2_EINVAL, "b2_broadcast: root %d out of range", root);
+  if (bytes == 0 || c->d.world == 1) return B2_OK;
+  if (!buf) return fail(B2_EINVAL, "b2_broadcast: null buffer");
+  if (*reinterpret_cast<volatile uint32_t*>(c->status_host) != 0)
+    return fail(B2_ESTATE, "communicator poisoned by an earlier peer-wait timeout");
+  DeviceGuard g(c->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t cap = c->stage_bytes & ~static_cast<size_t>(15);
+  uint8_t* p = static_cast<uint8_t*>(buf);
+  size_t left = bytes;
+  while (left > 0) {
+    const size_t n = left < cap ? left : cap;
+    const int grid = grid_for(c, (n + 15) / 16, 1);
+    k_broadcast<<<grid, kThreads, 0, s>>>(c->d, p, n, root);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B2_ECUDA, "broadcast kernel launch: %s", cudaGetErrorString(e));
+    c->launches++;
+    p += n;
+    left -= n;
+  }
+  return B2_OK;
+}
+
+int b2_barrier(b2_comm_t* c, void* stream) {
+  if (!c) return fail(B2_EINVAL, "null communicator");
+  if (c->d.world == 1) return B2_OK;
+  if (*reinterpret_cast<volatile uint32_t*>(c->status_host) != 0)
+    return fail(B2_ESTATE, "communicator poisoned by an earlier peer-wait timeout");
+  DeviceGuard g(c->device);
+  k_barrier<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(c->d);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(B2_ECUDA, "barrier kernel launch: %s", cudaGetErrorString(e));
+  c->launches++;
+  return B2_OK;
+}
+
+}  // extern "C"
