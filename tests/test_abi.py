@@ -1,0 +1,45 @@
+"""The C-ABI library loads and exports every symbol include/b200ddp.h declares (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+from torchx_b200.ddp import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "b200ddp.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_list_the_same_symbols():
+    assert _declared() == sorted(N.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    N.build_library()
+    L = ctypes.CDLL(N.LIB_PATH)
+    for s in _declared():
+        assert hasattr(L, s), s
+    assert N.lib().b2_version() == N.B2_ABI_VERSION
+
+
+def test_header_constants_match_binding():
+    src = open(os.path.join(ROOT, "include", "b200ddp.h")).read()
+    for name in ("B2_OK", "B2_EINVAL", "B2_ECUDA", "B2_ESYS", "B2_ETIMEOUT", "B2_ENOPEER", "B2_ESTATE", "B2_F32_WIRE_BF16",
+                 "B2_F32", "B2_BF16", "B2_ALGO_AUTO", "B2_ALGO_ONESHOT", "B2_ALGO_TWOSHOT", "B2_ABI_VERSION", "B2_MAX_WORLD"):
+        m = re.search(rf"#define\s+{name}\s+\(?(-?\d+)\)?", src)
+        assert m, name
+        assert int(m.group(1)) == getattr(N, name), name
+
+
+def test_argument_validation_without_a_gpu():
+    L = N.lib()
+    out = ctypes.c_void_p()
+    assert L.b2_comm_create(ctypes.byref(out), 3, 2, 0, b"/x", 0, 0, 10) == N.B2_EINVAL
+    assert b"bad arguments" in L.b2_last_error()
+    assert L.b2_allreduce(None, None, 8, 0, 1.0, 0, None) == N.B2_EINVAL
+    assert L.b2_comm_status(None) == N.B2_EINVAL
+    assert L.b2_comm_destroy(None) == N.B2_OK
