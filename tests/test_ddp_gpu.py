@@ -103,35 +103,65 @@ def test_no_sync_accumulates_locally_and_fp32_wire():
             c.close()
 
 
+def _run_ranks(W, fn):
+    """One host thread per rank, like the real one-process-per-GPU topology: a host-side sync inside one rank's
+    step (cuDNN handle/workspace setup, allocator) must not stop the other ranks from launching their kernels."""
+    import threading
+
+    errs = []
+
+    def body(r):
+        try:
+            fn(r)
+        except BaseException as e:  # noqa: BLE001
+            errs.append((r, e))
+
+    ts = [threading.Thread(target=body, args=(r,)) for r in range(W)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    if errs:
+        raise errs[0][1]
+
+
 def test_buffers_follow_rank0_every_forward():
     from torchx_b200.ddp import Communicator, DistributedDataParallel
 
     comms = Communicator.create_local([0, 0], stage_mb=8)
     try:
         streams = [torch.cuda.Stream() for _ in range(2)]
-        ddps = []
+        nets = []
         for r in range(2):
-            c = comms[r]
-            c.set_timeout(20.0)
-            c.set_max_ctas(8)
+            comms[r].set_timeout(20.0)
+            comms[r].set_max_ctas(8)
             torch.manual_seed(r)
             net = nn.Sequential(nn.Conv2d(3, 8, 3), nn.BatchNorm2d(8), nn.ReLU(), nn.Flatten(), nn.LazyLinear(4)).cuda()
             net(torch.zeros(2, 3, 8, 8, device="cuda"))  # materialise the lazy layer
-            with torch.cuda.stream(streams[r]):
-                ddps.append(DistributedDataParallel(net, c))
+            nets.append(net)
         torch.cuda.synchronize()
-        for step in range(2):
-            for r in range(2):
-                with torch.cuda.stream(streams[r]):
+        ddps = [None, None]
+
+        def build(r):
+            with torch.cuda.stream(streams[r]):
+                ddps[r] = DistributedDataParallel(nets[r], comms[r])
+                streams[r].synchronize()
+
+        _run_ranks(2, build)
+
+        def train(r):
+            with torch.cuda.stream(streams[r]):
+                for step in range(2):
                     x = torch.randn(4, 3, 8, 8, device="cuda") * (r + 1)
                     ddps[r](x).sum().backward()
-            torch.cuda.synchronize()
-        # after the next forward's sync both ranks hold rank 0's running stats (distributed.py:2176-2243)
-        for r in range(2):
-            with torch.cuda.stream(streams[r]):
-                ddps[r]._sync_buffers()
-        torch.cuda.synchronize()
+                ddps[r]._sync_buffers()  # what the next forward would do (distributed.py:2176-2243)
+                streams[r].synchronize()
+
+        _run_ranks(2, train)
+        for c in comms:
+            c.check()
         b0 = dict(ddps[0].module.named_buffers())
+        assert b0["1.num_batches_tracked"].item() == 3  # lazy-init forward + 2 training forwards, rank 0's count
         for name, b in ddps[1].module.named_buffers():
             assert torch.equal(b, b0[name]), name
     finally:

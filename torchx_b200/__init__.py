@@ -5,3 +5,7 @@ Launcher side mirrors meta-pytorch/torchx (``specs``, ``schedulers``, ``componen
 ``libb200ddp.so`` (hand-written sm_100a kernels, include/b200ddp.h).
 """
 from .version import __version__  # noqa: F401
+
+# Default "image" recorded in AppDefs.  The local schedulers ignore it (the cwd is the image) but components keep
+# the field so AppDefs are interchangeable with TorchX's (reference torchx/version.py TORCHX_IMAGE).
+IMAGE = f"ghcr.io/pytorch/torchx:{__version__}"

@@ -23,10 +23,19 @@ from .bucketing import MIB, BucketSpec, plan_buckets
 from .comm import Communicator
 
 
-def _view_like(flat_slice: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
-    from torch._prims_common import is_non_overlapping_and_dense
+def _dense_non_overlapping(t: torch.Tensor) -> bool:
+    """True if the tensor's elements tile a contiguous block exactly once in SOME dimension order
+    (contiguous, channels_last, any permutation)."""
+    expected = 1
+    for stride, size in sorted((st, sz) for sz, st in zip(t.shape, t.stride()) if sz != 1):
+        if stride != expected:
+            return False
+        expected *= size
+    return True
 
-    if p.is_contiguous() or not is_non_overlapping_and_dense(p):
+
+def _view_like(flat_slice: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
+    if p.is_contiguous() or not _dense_non_overlapping(p):
         return flat_slice.view(p.shape)
     return flat_slice.as_strided(p.shape, p.stride())
 

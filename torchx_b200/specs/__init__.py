@@ -1,0 +1,83 @@
+"""``torchx_b200.specs`` - the data model components and schedulers share (reference torchx/specs/__init__.py)."""
+from typing import Callable, Dict, Optional
+
+from .api import (  # noqa: F401
+    ALL,
+    MISSING,
+    NONE,
+    NULL_RESOURCE,
+    AppDef,
+    AppDryRunInfo,
+    AppHandle,
+    AppState,
+    AppStatus,
+    AppStatusError,
+    CfgVal,
+    InvalidRunConfigException,
+    MalformedAppHandleException,
+    ParsedAppHandle,
+    ReplicaState,
+    ReplicaStatus,
+    Resource,
+    RetryPolicy,
+    Role,
+    RoleStatus,
+    UnknownAppException,
+    UnknownSchedulerException,
+    cases,
+    get_type_name,
+    is_started,
+    is_terminal,
+    macros,
+    make_app_handle,
+    parse_app_handle,
+    runopt,
+    runopts,
+)
+from .named_resources import NAMED_RESOURCES as _GENERIC
+
+GiB: int = 1024
+
+
+def _all_named_resources() -> Dict[str, Callable[[], Resource]]:
+    merged: Dict[str, Callable[[], Resource]] = dict(_GENERIC)
+    try:
+        from torchx_b200.plugins import registered_named_resources
+
+        merged.update(registered_named_resources())
+    except Exception:  # pragma: no cover - plugin discovery must never break the core
+        pass
+    return merged
+
+
+class _NamedResources:
+    """Lazy mapping so plugin-registered resources show up without import-order games."""
+
+    def __getitem__(self, key: str) -> Resource:
+        table = _all_named_resources()
+        if key.upper() == "MISSING":
+            return NULL_RESOURCE
+        if key not in table:
+            raise KeyError(f"No named resource found for `{key}`. Registered named resources: {sorted(table)}")
+        return table[key]()
+
+    def __contains__(self, key: str) -> bool:
+        return key in _all_named_resources()
+
+    def keys(self):
+        return _all_named_resources().keys()
+
+
+named_resources = _NamedResources()
+
+
+def resource(cpu: Optional[int] = None, gpu: Optional[int] = None, memMB: Optional[int] = None, h: Optional[str] = None) -> Resource:
+    """``h`` (a named resource) wins over the raw values; unset raw values default to cpu=1, gpu=0, memMB=1024
+    (reference torchx/specs/__init__.py:148-181)."""
+    if h:
+        return named_resources[h]
+    return Resource(cpu=cpu if cpu is not None else 1, gpu=gpu if gpu is not None else 0, memMB=memMB if memMB is not None else 1024)
+
+
+def get_named_resources(res: str) -> Resource:
+    return named_resources[res]
