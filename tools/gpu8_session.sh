@@ -8,7 +8,7 @@ timeout 600 python -m pytest tests -m gpu -x -q --timeout 300 -k "across_devices
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu8.log; tail -3 gpurun_out/pytest_gpu8.log
 for W in 8 4; do
   timeout 500 $TR --nproc-per-node $W --master-port $((29600+W)) tools/sweep_allreduce.py --ctas 0,32,128 --algos auto,oneshot,twoshot \
-     --max-mib ${SWEEP_MAX_MIB:-512} --out gpurun_out/sweep_w$W.jsonl > gpurun_out/sweep_w$W.log 2>&1
+     --max-mib ${SWEEP_MAX_MIB:-1024} --out gpurun_out/sweep_w$W.jsonl > gpurun_out/sweep_w$W.log 2>&1
   echo "sweep W=$W rc=$?"; tail -2 gpurun_out/sweep_w$W.log | cut -c1-300
 done
 for N in 8; do

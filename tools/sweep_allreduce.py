@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--algos", default="auto")
     ap.add_argument("--extra-mib", default="7.82,30.04,25.04,25.32,9.27,27.04,168.27", help="DDP bucket sizes (SURVEY 8a)")
     ap.add_argument("--skip-nccl", action="store_true")
+    ap.add_argument("--oneshot-max-mib", type=float, default=32.0, help="do not time the forced one-shot algorithm above this size")
     ap.add_argument("--out", default="")
     a = ap.parse_args()
 
@@ -88,6 +89,8 @@ def main():
         for ctas in [int(v) for v in a.ctas.split(",")]:
             comm.set_max_ctas(ctas)
             for algo in a.algos.split(","):
+                if algo == "oneshot" and S > a.oneshot_max_mib * (1 << 20):
+                    continue
                 t = time_op(lambda b: comm.allreduce_(b, algo=algo, stream=stream), bufs, iters, warm, stream)
                 key = f"ours_fused[{algo},ctas={ctas}]"
                 row[key] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1), "hbm_alg_gbs": round(8 * n / t / 1e9, 1)}

@@ -1,0 +1,567 @@
+"""``local_cuda``: the B200-native single-box scheduler.  One worker process per GPU, spawned directly.
+
+It accepts the UNMODIFIED ``dist.ddp`` AppDef (``bash -c "torchrun ... --nproc_per_node N script.py"``, reference
+torchx/components/dist.py:261-308) and replaces what ``local_cwd`` + ``torchrun`` do with it
+(reference schedulers/local_scheduler.py:947-1022 + torch/distributed/elastic/agent/server/local_elastic_agent.py:309-323):
+
+  * parses the torchrun command line back into (nnodes, nproc_per_node, script|-m module, args) and spawns the
+    ``nnodes x nproc_per_node`` workers itself - no bash, no elastic agent, no c10d rendezvous round trips;
+  * gives every worker the full torchrun environment contract (RANK, LOCAL_RANK, WORLD_SIZE, LOCAL_WORLD_SIZE,
+    GROUP_RANK, GROUP_WORLD_SIZE, ROLE_RANK, ROLE_WORLD_SIZE, ROLE_NAME, MASTER_ADDR, MASTER_PORT,
+    TORCHELASTIC_RESTART_COUNT / MAX_RESTARTS / RUN_ID / USE_AGENT_STORE / ERROR_FILE, OMP_NUM_THREADS) so existing
+    scripts (``torchx.distributed.init_pg``, plain ``init_process_group("nccl")``) run unchanged;
+  * pins each rank: ``B2_DEVICE`` = its CUDA ordinal, CPU affinity = the cores of that GPU's NUMA node split among the
+    node's ranks;
+  * hands out the peer-buffer rendezvous instead of a TCP store: ``B2_SHM_NAME=/b2_<app_id>`` + ``B2_EPOCH=<attempt>``
+    name the POSIX-shm control block through which ``libb200ddp.so`` exchanges CUDA-IPC handles (include/b200ddp.h);
+  * NEW behaviour the reference's local scheduler lacks (its num_restarts is hard-coded 0, local_scheduler.py:1057):
+    ``Role.max_retries`` is honoured - when a worker dies the gang is torn down and re-launched with the next epoch
+    (fresh shm name, TORCHELASTIC_RESTART_COUNT+1), so survivors never touch a dead peer's memory;
+  * keeps the on-disk contract: ``<log_dir>/<session>/<app_id>/<role>/<replica>/{stdout,stderr,combined}.log`` now hold
+    the ``[rank]:``-prefixed merge of the workers' streams (what ``--tee 3`` prints), per-worker files live under
+    ``attempt_<n>/rank_<local_rank>/``; ``error.json`` / ``SUCCESS`` as before, so ``torchx log|status`` work unchanged.
+
+Roles whose command is not a torchrun line (e.g. ``utils.echo``) are launched exactly as ``local_cwd`` would.
+"""
+from __future__ import annotations
+
+import io
+import logging
+import os
+import pprint
+import shlex
+import socket
+import subprocess
+import sys
+import threading
+import time
+from dataclasses import asdict, dataclass, field
+from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
+
+from torchx_b200.schedulers.api import DescribeAppResponse
+from torchx_b200.schedulers.local_scheduler import (
+    COMBINED_LOG,
+    ENV_CUDA_VISIBLE_DEVICES,
+    NA,
+    STDERR_LOG,
+    STDOUT_LOG,
+    CWDImageProvider,
+    ImageProvider,
+    LocalOpts,
+    LocalScheduler,
+    Opts,
+    PopenRequest,
+    ReplicaParam,
+    _LocalAppDef,
+    _LocalReplica,
+)
+from torchx_b200.schedulers.ids import make_unique
+from torchx_b200.specs.api import AppDef, AppDryRunInfo, AppState, Role, is_terminal, runopts
+
+log = logging.getLogger(__name__)
+
+MONITOR_POLL_S = 0.1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# run options
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class CudaOpts(Opts):
+    devices: Optional[List[str]] = None
+    """CUDA ordinals this job may use, in rank order (default: all GPUs reported by nvidia-smi)."""
+
+    pin_cpus: bool = True
+    """Bind each worker to its GPU's NUMA-local cores (split evenly among the ranks sharing the node)."""
+
+    omp_num_threads: int = 1
+    """OMP_NUM_THREADS for workers that do not set it (torchrun's default is 1)."""
+
+    stage_mb: int = 0
+    """Per-rank staging buffer size in MiB for the peer-buffer allreduce (0 = library default 128)."""
+
+    master_port: int = 0
+    """MASTER_PORT handed to the workers (0 = pick a free port at launch)."""
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# torchrun command line -> spec
+# ---------------------------------------------------------------------------------------------------------------
+_VALUE_OPTS = {
+    "--rdzv_backend", "--rdzv_conf", "--rdzv_endpoint", "--rdzv_id", "--nnodes", "--nproc_per_node", "--tee", "-t", "--role",
+    "--node_rank", "--max_restarts", "--master_addr", "--master_port", "--log_dir", "--redirects", "-r", "--monitor_interval",
+    "--start_method", "--local_addr", "--local_ranks_filter", "--logs_specs", "--event_log_handler",
+}
+_FLAG_OPTS = {"--standalone", "--no_python", "--run_path"}
+
+
+@dataclass
+class TorchrunSpec:
+    """What ``dist.ddp`` asked torchrun to do, recovered from the command line it emitted."""
+
+    min_nnodes: int = 1
+    max_nnodes: int = 1
+    nproc_per_node: str = "1"  # an int literal, or "gpu"/"auto" (resolved against the device count)
+    rdzv_id: str = ""
+    role: str = ""
+    tee: int = 0
+    node_rank: Optional[int] = None
+    max_restarts: Optional[int] = None
+    module: Optional[str] = None
+    script: Optional[str] = None
+    no_python: bool = False
+    script_args: List[str] = field(default_factory=list)
+
+    def worker_cmd(self) -> List[str]:
+        if self.module is not None:
+            return [sys.executable, "-u", "-m", self.module, *self.script_args]
+        assert self.script is not None
+        if self.no_python:
+            return [self.script, *self.script_args]
+        return [sys.executable, "-u", self.script, *self.script_args]
+
+
+def parse_torchrun(cmdline: str) -> Optional[TorchrunSpec]:
+    """``None`` if ``cmdline`` is not a torchrun invocation; raises ``ValueError`` for a torchrun line this
+    scheduler cannot honour."""
+    try:
+        toks = shlex.split(cmdline)
+    except ValueError:
+        return None
+    if toks[:1] == ["torchrun"]:
+        toks = toks[1:]
+    elif len(toks) >= 3 and os.path.basename(toks[0]).startswith("python") and toks[1:3] == ["-m", "torch.distributed.run"]:
+        toks = toks[3:]
+    else:
+        return None
+    spec = TorchrunSpec()
+    i = 0
+    while i < len(toks):
+        tok = toks[i]
+        key, eq, inline = tok.partition("=")
+        if key.startswith("--"):  # torchrun accepts both --nproc-per-node and --nproc_per_node
+            key = "--" + key[2:].replace("-", "_")
+        if key in ("-m", "--module"):
+            if i + 1 >= len(toks):
+                raise ValueError("torchrun -m needs a module name")
+            spec.module, spec.script_args = toks[i + 1], toks[i + 2:]
+            return spec
+        if key in _FLAG_OPTS:
+            if key == "--no_python":
+                spec.no_python = True
+            i += 1
+            continue
+        if key in _VALUE_OPTS:
+            if eq:
+                val, step = inline, 1
+            else:
+                if i + 1 >= len(toks):
+                    raise ValueError(f"torchrun option {tok} needs a value")
+                val, step = toks[i + 1], 2
+            if key == "--nnodes":
+                lo, _, hi = val.partition(":")
+                spec.min_nnodes, spec.max_nnodes = int(lo), int(hi or lo)
+            elif key == "--nproc_per_node":
+                spec.nproc_per_node = val
+            elif key == "--rdzv_id":
+                spec.rdzv_id = val
+            elif key == "--role":
+                spec.role = val
+            elif key in ("--tee", "-t"):
+                spec.tee = int(val) if val.isdigit() else 0
+            elif key == "--node_rank":
+                spec.node_rank = int(val)
+            elif key == "--max_restarts":
+                spec.max_restarts = int(val)
+            i += step
+            continue
+        if tok.startswith("-"):
+            raise ValueError(f"local_cuda cannot interpret torchrun option {tok!r} in: {cmdline}")
+        spec.script, spec.script_args = tok, toks[i + 1:]
+        return spec
+    raise ValueError(f"no training script or module in torchrun command: {cmdline}")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# request
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class WorkerGroup:
+    """The workers one replica ("node") expands to."""
+
+    role_name: str
+    replica_id: int
+    is_torchrun: bool
+    nproc: int
+    devices: List[int]  # CUDA ordinal per local rank (as seen by the worker, after CUDA_VISIBLE_DEVICES)
+    cpu_sets: List[List[int]]  # affinity per local rank ([] = leave alone)
+    cmd: List[str]
+    env: Dict[str, str]  # node-level env (role env + local scheduler additions)
+    rank_offset: int = 0
+    world_size: int = 1
+    group_world_size: int = 1
+    cwd: Optional[str] = None
+    role_label: str = ""
+
+
+@dataclass
+class CudaPopenRequest(PopenRequest):
+    groups: Dict[str, List[WorkerGroup]] = field(default_factory=dict)
+    max_retries: int = 0
+    shm_name: str = ""
+    master_port: int = 0
+    stage_mb: int = 0
+    omp_num_threads: int = 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# replica-level log multiplexer
+# ---------------------------------------------------------------------------------------------------------------
+class _ReplicaLogMux:
+    """Follows the per-worker stdout/stderr files of one replica (across attempts) and writes the ``[rank]:``-prefixed
+    merge into the replica-level stdout.log / stderr.log / combined.log that ``torchx log`` reads."""
+
+    def __init__(self, stdout_path: str, stderr_path: str, combined_path: str) -> None:
+        os.makedirs(os.path.dirname(stdout_path), exist_ok=True)
+        self._sinks = {"out": io.open(stdout_path, "ab", buffering=0), "err": io.open(stderr_path, "ab", buffering=0)}
+        self._combined = io.open(combined_path, "ab", buffering=0)
+        self._lock = threading.Lock()
+        self._sources: List[Dict[str, Any]] = []
+        self._closed = False
+        self._thread = threading.Thread(target=self._pump, name="replica-log-mux", daemon=True)
+        self._thread.start()
+
+    def add_source(self, path: str, kind: str, prefix: bytes) -> None:
+        with self._lock:
+            self._sources.append({"path": path, "kind": kind, "prefix": prefix, "fd": None, "tail": b""})
+
+    def _drain(self) -> bool:
+        moved = False
+        with self._lock:
+            sources = list(self._sources)
+        for src in sources:
+            if src["fd"] is None:
+                if not os.path.exists(src["path"]):
+                    continue
+                src["fd"] = io.open(src["path"], "rb", buffering=0)
+            data = src["fd"].read(1 << 16)
+            if not data:
+                continue
+            moved = True
+            data = src["tail"] + data
+            lines = data.split(b"\n")
+            src["tail"] = lines.pop()
+            if lines:
+                blob = b"".join(src["prefix"] + ln + b"\n" for ln in lines)
+                self._sinks[src["kind"]].write(blob)
+                self._combined.write(blob)
+        return moved
+
+    def _pump(self) -> None:
+        while True:
+            if not self._drain():
+                if self._closed:
+                    break
+                time.sleep(0.05)
+        for src in self._sources:
+            if src["tail"]:
+                blob = src["prefix"] + src["tail"] + b"\n"
+                self._sinks[src["kind"]].write(blob)
+                self._combined.write(blob)
+                src["tail"] = b""
+
+    def close(self) -> None:
+        if self._closed:
+            return
+        self._closed = True
+        self._thread.join()
+        for src in self._sources:
+            if src["fd"] is not None:
+                src["fd"].close()
+        for f in (*self._sinks.values(), self._combined):
+            f.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host topology (best effort; everything degrades to "don't pin")
+# ---------------------------------------------------------------------------------------------------------------
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.extend(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def gpu_numa_cpus(device: int) -> List[int]:
+    """Cores local to ``device``'s NUMA node, from nvidia-smi's PCI bus id and sysfs.  [] if unknown."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(device)],
+                             capture_output=True, text=True, check=True, timeout=20).stdout.strip()
+        bus = out.splitlines()[0].strip().lower()
+        if bus.count(":") == 2 and len(bus.split(":")[0]) == 8:
+            bus = bus[4:]  # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return []
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            allowed = set(os.sched_getaffinity(0))
+            return [c for c in _parse_cpulist(f.read()) if c in allowed]
+    except Exception:  # noqa: BLE001 - any failure just means "no pinning"
+        return []
+
+
+def _free_port() -> int:
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return int(s.getsockname()[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# app bookkeeping
+# ---------------------------------------------------------------------------------------------------------------
+class _CudaApp(_LocalAppDef):
+    def __init__(self, id: str, log_dir: str, request: CudaPopenRequest) -> None:
+        super().__init__(id, log_dir)
+        self.request = request
+        self.muxes: List[_ReplicaLogMux] = []
+        self.monitor: Optional[threading.Thread] = None
+        self.stop_monitor = threading.Event()
+        self.failure_msg = ""
+
+
+class LocalCudaScheduler(LocalScheduler):
+    def __init__(self, session_name: str, image_provider_class: Callable[[LocalOpts], ImageProvider] = CWDImageProvider,
+                 cache_size: int = 100, extra_paths: Optional[List[str]] = None) -> None:
+        super().__init__(session_name, image_provider_class, cache_size, extra_paths, backend="local_cuda")
+
+    # -- options ----------------------------------------------------------------------------------------------------
+    def _run_opts(self) -> runopts:
+        return CudaOpts.as_runopts()
+
+    def _opts(self, cfg: LocalOpts) -> CudaOpts:  # type: ignore[override]
+        return cfg if isinstance(cfg, CudaOpts) else CudaOpts.from_cfg(cfg)
+
+    def _numa_cpus(self, device: int) -> List[int]:
+        return gpu_numa_cpus(device)
+
+    # -- request construction (pure: no dirs, no processes, no sockets) -------------------------------------------------
+    def _device_pool(self, opts: CudaOpts) -> List[int]:
+        if opts.devices:
+            return [int(d) for d in opts.devices]
+        return list(range(self._cuda_device_count()))
+
+    def _to_popen_request(self, app: AppDef, cfg: LocalOpts) -> CudaPopenRequest:  # type: ignore[override]
+        opts = self._opts(cfg)
+        app_id = make_unique(app.name)
+        provider = self._image_provider_class(cfg)
+        app_log_dir = self._get_app_log_dir(app_id, opts)
+        pool = self._device_pool(opts)
+        cursor = 0  # next unclaimed entry of the device pool
+        role_params: Dict[str, List[ReplicaParam]] = {}
+        role_log_dirs: Dict[str, List[str]] = {}
+        groups: Dict[str, List[WorkerGroup]] = {}
+        max_retries = 0
+        for role in app.roles:
+            max_retries = max(max_retries, role.max_retries)
+            params = role_params.setdefault(role.name, [])
+            log_dirs = role_log_dirs.setdefault(role.name, [])
+            role_groups = groups.setdefault(role.name, [])
+            img_root = provider.fetch_role(role)
+            cwd = provider.get_cwd(role.image)
+            role.env["PATH"] = self._role_path_env(role, cwd, opts)
+            for replica_id in range(role.num_replicas):
+                rr, replica_log_dir = self._replica_role(role, img_root, app_id, replica_id, app_log_dir)
+                node = provider.get_replica_param(img_root, rr, os.path.join(replica_log_dir, STDOUT_LOG),
+                                                  os.path.join(replica_log_dir, STDERR_LOG), os.path.join(replica_log_dir, COMBINED_LOG))
+                params.append(node)
+                log_dirs.append(replica_log_dir)
+                spec = None
+                if rr.entrypoint == "bash" and len(rr.args) == 2 and rr.args[0] == "-c":
+                    spec = parse_torchrun(rr.args[1])
+                if spec is None:
+                    role_groups.append(WorkerGroup(role.name, replica_id, False, 1, [-1], [[]], list(node.args), dict(node.env), cwd=node.cwd))
+                    continue
+                if spec.nproc_per_node in ("gpu", "auto"):
+                    nproc = max(1, role.resource.gpu if role.resource.gpu > 0 else len(pool) // max(role.num_replicas, 1))
+                else:
+                    nproc = int(spec.nproc_per_node)
+                wants_gpu = role.resource.gpu > 0 or len(pool) >= cursor + nproc
+                devices: List[int] = []
+                env = dict(node.env)
+                if wants_gpu and len(pool) >= cursor + nproc:
+                    mine = pool[cursor: cursor + nproc]
+                    cursor += nproc
+                    if role.num_replicas > 1:
+                        # several "nodes" on one box: give each its own visible set so LOCAL_RANK -> cuda:LOCAL_RANK holds
+                        env[ENV_CUDA_VISIBLE_DEVICES] = ",".join(str(d) for d in mine)
+                        devices = list(range(nproc))
+                    else:
+                        devices = mine
+                    physical = mine
+                else:
+                    if role.resource.gpu > 0 and pool:
+                        raise ValueError(f"role {role.name!r} replica {replica_id} needs {nproc} GPUs but only {max(len(pool) - cursor, 0)} of {len(pool)} remain")
+                    devices, physical = [-1] * nproc, []  # CPU job (gloo): no pinning
+                cpu_sets: List[List[int]] = [[] for _ in range(nproc)]
+                if opts.pin_cpus and physical:
+                    by_node: Dict[Tuple[int, ...], List[int]] = {}
+                    for lr, dev in enumerate(physical):
+                        by_node.setdefault(tuple(self._numa_cpus(dev)), []).append(lr)
+                    for cpus, ranks in by_node.items():
+                        if not cpus:
+                            continue
+                        share = max(len(cpus) // len(ranks), 1)
+                        for k, lr in enumerate(ranks):
+                            cpu_sets[lr] = list(cpus[k * share: (k + 1) * share]) or list(cpus)
+                role_groups.append(WorkerGroup(role.name, replica_id, True, nproc, devices, cpu_sets, spec.worker_cmd(), env, cwd=node.cwd,
+                                               role_label=spec.role))
+            # ranks: replicas of a role are consecutive "nodes"
+            tr = [g for g in role_groups if g.is_torchrun]
+            world = sum(g.nproc for g in tr)
+            offset = 0
+            for g in tr:
+                g.rank_offset, g.world_size, g.group_world_size = offset, world, len(tr)
+                offset += g.nproc
+        return CudaPopenRequest(app_id, app_log_dir, role_params, role_log_dirs, groups=groups, max_retries=max_retries,
+                                shm_name=f"/b2_{app_id}"[:200], master_port=opts.master_port, stage_mb=opts.stage_mb,
+                                omp_num_threads=opts.omp_num_threads)
+
+    def _submit_dryrun(self, app: AppDef, cfg: LocalOpts) -> AppDryRunInfo[CudaPopenRequest]:  # type: ignore[override]
+        return AppDryRunInfo(self._to_popen_request(app, cfg), lambda req: pprint.pformat(asdict(req), indent=2, width=100))
+
+    # -- launching ----------------------------------------------------------------------------------------------------
+    def _worker_env(self, req: CudaPopenRequest, g: WorkerGroup, local_rank: int, attempt: int, error_file: str) -> Dict[str, str]:
+        """The torchrun contract (local_elastic_agent.py:309-323) plus the peer-buffer rendezvous variables."""
+        env = dict(g.env)
+        rank = g.rank_offset + local_rank
+        env.update({
+            "RANK": str(rank), "LOCAL_RANK": str(local_rank), "GROUP_RANK": str(g.replica_id), "ROLE_RANK": str(rank),
+            "ROLE_NAME": g.role_label, "LOCAL_WORLD_SIZE": str(g.nproc), "WORLD_SIZE": str(g.world_size),
+            "GROUP_WORLD_SIZE": str(g.group_world_size), "ROLE_WORLD_SIZE": str(g.world_size),
+            "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(req.master_port),
+            "TORCHELASTIC_RESTART_COUNT": str(attempt), "TORCHELASTIC_MAX_RESTARTS": str(req.max_retries),
+            "TORCHELASTIC_RUN_ID": req.app_id, "TORCHELASTIC_USE_AGENT_STORE": "False",
+            "TORCH_NCCL_ASYNC_ERROR_HANDLING": os.getenv("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1"),
+            "TORCHELASTIC_ERROR_FILE": error_file,
+            "B2_SHM_NAME": f"{req.shm_name}_{g.role_name}"[:240], "B2_EPOCH": str(attempt),
+        })
+        if g.devices[local_rank] >= 0:
+            env["B2_DEVICE"] = str(g.devices[local_rank])
+        if req.stage_mb:
+            env["B2_STAGE_MB"] = str(req.stage_mb)
+        if "OMP_NUM_THREADS" not in env and "OMP_NUM_THREADS" not in os.environ:
+            env["OMP_NUM_THREADS"] = str(req.omp_num_threads)
+        return env
+
+    def _spawn_attempt(self, app: _CudaApp, attempt: int) -> None:
+        req = app.request
+        app.role_replicas = {}
+        for role_name, role_groups in req.groups.items():
+            for g, mux in zip(role_groups, [m for m in app.muxes if m.role == role_name]):  # type: ignore[attr-defined]
+                replica_dir = req.role_log_dirs[role_name][g.replica_id]
+                for lr in range(g.nproc):
+                    if g.is_torchrun:
+                        wdir = os.path.join(replica_dir, f"attempt_{attempt}", f"rank_{lr}")
+                        prefix = f"[{g.rank_offset + lr}]:".encode()
+                    else:
+                        wdir = os.path.join(replica_dir, f"attempt_{attempt}")
+                        prefix = b""
+                    os.makedirs(wdir, exist_ok=True)
+                    out, err = os.path.join(wdir, STDOUT_LOG), os.path.join(wdir, STDERR_LOG)
+                    # the replica-level error.json stays the root-cause file of the LATEST attempt
+                    error_file = os.path.join(wdir, "error.json")
+                    env = self._worker_env(req, g, lr, attempt, error_file) if g.is_torchrun else dict(g.env)
+                    p = ReplicaParam(g.cmd, env, out, err, None, g.cwd)
+                    cpus = g.cpu_sets[lr] if lr < len(g.cpu_sets) else []
+                    preexec = (lambda c=tuple(cpus): os.sched_setaffinity(0, c)) if cpus else None
+                    rep = self._popen(role_name, g.replica_id, p, preexec_fn=preexec)
+                    app.add_replica(role_name, rep)
+                    mux.add_source(out, "out", prefix)
+                    mux.add_source(err, "err", prefix)
+
+    def schedule(self, dryrun_info: AppDryRunInfo[CudaPopenRequest]) -> str:  # type: ignore[override]
+        req: CudaPopenRequest = dryrun_info.request
+        if req.master_port == 0:
+            req.master_port = _free_port()
+        with self._apps_lock:
+            self._reserve_slot(req.app_id)
+            os.makedirs(req.log_dir)
+            app = _CudaApp(req.app_id, req.log_dir, req)
+            for role_name, params in req.role_params.items():
+                for replica_id, node in enumerate(params):
+                    os.makedirs(req.role_log_dirs[role_name][replica_id])
+                    mux = _ReplicaLogMux(node.stdout, node.stderr, node.combined)  # type: ignore[arg-type]
+                    mux.role = role_name  # type: ignore[attr-defined]
+                    app.muxes.append(mux)
+            app.extra_closers.append(lambda: [m.close() for m in app.muxes])
+            self._spawn_attempt(app, 0)
+            app.set_state(AppState.RUNNING)
+            self._apps[req.app_id] = app
+        app.monitor = threading.Thread(target=self._monitor, args=(app,), name=f"monitor-{req.app_id}", daemon=True)
+        app.monitor.start()
+        return req.app_id
+
+    # -- supervision --------------------------------------------------------------------------------------------------
+    def _monitor(self, app: _CudaApp) -> None:
+        """Gang supervision: any worker failure kills the attempt; with retries left the whole gang is re-launched
+        under the next epoch (RetryPolicy.APPLICATION semantics), otherwise the app is FAILED."""
+        while not app.stop_monitor.wait(MONITOR_POLL_S):
+            with app.lock:
+                if is_terminal(app.state):
+                    return
+                reps = app.replicas()
+                failed = [r for r in reps if r.failed()]
+                if failed:
+                    r0 = failed[0]
+                    app.failure_msg = f"{r0.role_name}[{r0.replica_id}] pid {r0.proc.pid} exited with code {r0.proc.returncode}"
+                    app.kill()
+                    if app.num_restarts < app.request.max_retries:
+                        app.num_restarts += 1
+                        log.warning("app %s: %s; re-launching (restart %d of %d)", app.id, app.failure_msg, app.num_restarts,
+                                    app.request.max_retries)
+                        self._spawn_attempt(app, app.num_restarts)
+                        continue
+                    app.set_state(AppState.FAILED)
+                    return
+                if reps and not any(r.is_alive() for r in reps):
+                    app.set_state(AppState.SUCCEEDED)
+                    return
+
+    def _refresh_state(self, app: _LocalAppDef) -> AppState:
+        return app.state  # the monitor thread owns state transitions
+
+    def describe(self, app_id: str) -> Optional[DescribeAppResponse]:
+        app = self._apps.get(app_id)
+        if app is None:
+            return None
+        with app.lock:
+            err = app.get_structured_error_msg()
+            if is_terminal(app.state):
+                app.close()
+            msg = getattr(app, "failure_msg", "")
+            return DescribeAppResponse(app_id=app_id, state=app.state, num_restarts=app.num_restarts, structured_error_msg=err,
+                                       ui_url=f"file://{app.log_dir}", msg=msg or "<NONE>")
+
+    def _cancel_existing(self, app_id: str) -> None:
+        app = self._apps[app_id]
+        if isinstance(app, _CudaApp):
+            app.stop_monitor.set()
+        with app.lock:
+            app.close()
+            app.state = AppState.CANCELLED
+
+    def close(self) -> None:
+        for app in list(self._apps.values()):
+            if isinstance(app, _CudaApp):
+                app.stop_monitor.set()
+        super().close()
+
+
+def create_scheduler(session_name: str, cache_size: int = 100, extra_paths: Optional[List[str]] = None,
+                     image_provider_class: Callable[[LocalOpts], ImageProvider] = CWDImageProvider, **kwargs: Any) -> LocalCudaScheduler:
+    return LocalCudaScheduler(session_name=session_name, image_provider_class=image_provider_class, cache_size=cache_size,
+                              extra_paths=extra_paths)
