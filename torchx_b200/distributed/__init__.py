@@ -1,0 +1,124 @@
+"""Worker-side helpers, importable from the training script the launcher starts.
+
+Mirror of reference torchx/distributed/__init__.py (local_rank:26, local_cuda_device:57, local_device:70, rank:91,
+world_size:109, init_pg:164, on_rank0_first:231, on_local_rank0_first:278): rank/device discovery from the torchrun
+environment contract and barrier-ordered critical sections.  Two backends behind the same functions:
+
+  * a ``torch.distributed`` process group, exactly as the reference does (``init_pg("auto")`` -> nccl on GPU hosts, gloo
+    otherwise) - this is what config #1 (CPU/gloo) and unmodified TorchX scripts use;
+  * ``init_pg("b200")`` - the peer-buffer communicator from ``libb200ddp.so``: no TCP store, no NCCL.  ``barrier`` /
+    ``on_rank0_first`` then run on that fabric.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from contextlib import contextmanager
+from datetime import timedelta
+from typing import Any, Iterator, Optional
+
+import torch
+import torch.distributed as dist
+
+_COMM: Optional[Any] = None  # torchx_b200.ddp.Communicator when init_pg("b200") was used
+
+
+def local_rank() -> int:
+    """``LOCAL_RANK`` (0 when not launched by torchrun / local_cuda)."""
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def rank() -> int:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank()
+    return int(os.environ.get("RANK", "0")) if _COMM is None else _COMM.rank
+
+
+def world_size() -> int:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return int(os.environ.get("WORLD_SIZE", "1")) if _COMM is None else _COMM.world
+
+
+def local_cuda_device() -> torch.device:
+    """``cuda:$B2_DEVICE`` under ``local_cuda`` (the scheduler pins the device), else ``cuda:$LOCAL_RANK``."""
+    return torch.device("cuda", int(os.environ.get("B2_DEVICE", str(local_rank()))))
+
+
+def local_device() -> torch.device:
+    return local_cuda_device() if torch.cuda.is_available() else torch.device("cpu")
+
+
+def communicator() -> Any:
+    """The process-wide B200 communicator (``init_pg("b200")`` must have been called)."""
+    if _COMM is None:
+        raise RuntimeError('no B200 communicator: call torchx_b200.distributed.init_pg("b200") first')
+    return _COMM
+
+
+def is_torchelastic_launched() -> bool:
+    return "TORCHELASTIC_RUN_ID" in os.environ
+
+
+def init_pg(backend: str = "auto", **kwargs: Any) -> torch.device:
+    """Initialise this worker's collective backend and return the device it should use.
+
+    ``auto``: nccl when CUDA devices exist, gloo otherwise (reference behaviour).  When the process was not launched
+    by a torchrun-compatible launcher a trivial single-rank group is created so scripts also run with plain ``python``.
+    ``b200``: rendezvous through the ``local_cuda`` scheduler's shm control block and CUDA IPC; no process group.
+    """
+    global _COMM
+    if backend == "b200":
+        if _COMM is None:
+            from torchx_b200.ddp import Communicator
+
+            _COMM = Communicator.from_env(**kwargs)
+        return torch.device("cuda", _COMM.device)
+    if backend == "auto":
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if dist.is_initialized():
+        warnings.warn("the default process group is already initialized; init_pg() leaves it untouched")
+    elif is_torchelastic_launched():
+        dist.init_process_group(backend=backend, **kwargs)
+    else:
+        warnings.warn("not launched by torchrun/local_cuda: creating a trivial single-rank process group")
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "0")
+        dist.init_process_group(backend=backend, rank=0, world_size=1, **kwargs)
+    dev = local_device() if backend == "nccl" else torch.device("cpu")
+    if dev.type == "cuda":
+        torch.cuda.set_device(dev)
+    return dev
+
+
+def barrier() -> None:
+    if _COMM is not None and not dist.is_initialized():
+        _COMM.barrier()
+        torch.cuda.current_stream(_COMM.device).synchronize()
+    elif dist.is_initialized():
+        dist.barrier()
+
+
+@contextmanager
+def on_rank0_first() -> Iterator[None]:
+    """Run the block on rank 0 first, then on everyone else (download-once patterns)."""
+    if rank() != 0:
+        barrier()
+    try:
+        yield
+    finally:
+        if rank() == 0:
+            barrier()
+
+
+@contextmanager
+def on_local_rank0_first() -> Iterator[None]:
+    """Single-box topology: local rank 0 == rank 0 of its node; with one node this equals on_rank0_first()."""
+    first = local_rank() == 0
+    if not first:
+        barrier()
+    try:
+        yield
+    finally:
+        if first:
+            barrier()

@@ -70,12 +70,15 @@ class StructuredOpts(Mapping[str, CfgVal]):
     @classmethod
     def get_docstrings(cls) -> Dict[str, str]:
         docs: Dict[str, str] = {}
-        try:
-            src = inspect.getsource(cls)
-        except (OSError, TypeError):
-            src = ""
-        for name, text in _FIELD_DOC.findall(src):
-            docs[name] = " ".join(text.split())
+        for klass in reversed(cls.__mro__):  # inherited option groups keep their help text
+            if not _is_opts_class(klass):
+                continue
+            try:
+                src = inspect.getsource(klass)
+            except (OSError, TypeError):
+                continue
+            for name, text in _FIELD_DOC.findall(src):
+                docs[name] = " ".join(text.split())
         for f, tp in cls._typed_fields():
             if _is_opts_class(tp):
                 docs.update({f"{f.name}.{k}": v for k, v in tp.get_docstrings().items()})
