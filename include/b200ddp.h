@@ -116,6 +116,14 @@ int b2_comm_status(const b2_comm_t* comm);
 uint64_t b2_comm_launch_count(const b2_comm_t* comm);
 
 /*
+ * Measurement aid (tools/sweep_allreduce.py --trace): when enabled, thread 0 of every CTA of a collective records
+ * %globaltimer at its phase boundaries (8 u64 slots per CTA: start, scatter done, barrier 1 passed, reduce done,
+ * barrier 2 passed, gather done).  Calling with a non-NULL `out` first copies the stamps of the most recent
+ * collective for CTAs [0, max_ctas) (synchronously; call after a stream sync), then applies `enable`.
+ */
+int b2_comm_trace(b2_comm_t* comm, int enable, uint64_t* out, int max_ctas);
+
+/*
  * In-place averaged/scaled SUM allreduce of `n_elems` elements at device pointer `buf`
  * (any device allocation of this rank; it does not need to be symmetric memory):
  *      buf[i] <- round( sum_{r=0..W-1} wire( scale * buf_r[i] ) )

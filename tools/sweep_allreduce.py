@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--skip-nccl", action="store_true")
     ap.add_argument("--oneshot-max-mib", type=float, default=32.0, help="do not time the forced one-shot algorithm above this size")
     ap.add_argument("--out", default="")
+    ap.add_argument("--trace", action="store_true", help="record the per-CTA phase breakdown of one launch per size/algo")
     a = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -82,8 +83,8 @@ def main():
             y.copy_(c)
         stream.synchronize()
         comm.check()
-        denom = torch.maximum(x.abs(), y.abs()).clamp_min(1e-30)
-        row["max_rel_diff_vs_nccl_bf16"] = float(((x - y).abs() / denom).max().item()) if n else 0.0
+        # NCCL's reduction order is its own for W >= 4, so compare against the magnitude of the data, not per element
+        row["max_abs_diff_over_max_abs_vs_nccl_bf16"] = float(((x - y).abs().max() / y.abs().max().clamp_min(1e-30)).item()) if n else 0.0
         row["bit_equal_vs_nccl_bf16"] = bool(torch.equal(x, y))
 
         for ctas in [int(v) for v in a.ctas.split(",")]:
@@ -94,6 +95,22 @@ def main():
                 t = time_op(lambda b: comm.allreduce_(b, algo=algo, stream=stream), bufs, iters, warm, stream)
                 key = f"ours_fused[{algo},ctas={ctas}]"
                 row[key] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1), "hbm_alg_gbs": round(8 * n / t / 1e9, 1)}
+                if a.trace and algo != "auto":
+                    comm.trace(True)
+                    dist.barrier()
+                    comm.allreduce_(bufs[0], algo=algo, stream=stream)
+                    stream.synchronize()
+                    stamps = [st for st in comm.trace(False, read_ctas=296) if st[0]]
+                    if stamps:
+                        t0 = min(st[0] for st in stamps)
+                        last = 5 if algo == "twoshot" else 3
+                        names = ["scatter", "bar1", "reduce", "bar2", "gather"] if algo == "twoshot" else ["push", "bar1", "reduce"]
+                        med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
+                        row[key]["trace_us"] = {
+                            "ctas": len(stamps), "start_spread": round((max(st[0] for st in stamps) - t0) / 1e3, 2),
+                            **{nm: round(med([st[i + 1] - st[i] for st in stamps]) / 1e3, 2) for i, nm in enumerate(names)},
+                            "total": round((max(st[last] for st in stamps) - t0) / 1e3, 2),
+                        }
         comm.set_max_ctas(0)
         t = time_op(lambda b: comm.allreduce_(b, wire="f32", stream=stream), bufs, iters, warm, stream)
         row["ours_f32"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(4 * n / t * k / 1e9, 1)}

@@ -70,6 +70,8 @@ struct CommDev {
   unsigned long long stage_off[2];  // byte offsets of the two staging buffers inside an arena
   unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
                                     //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced"
+  unsigned long long* trace;        // optional (b2_comm_trace): per-CTA globaltimer stamps of the LAST collective,
+                                    // 8 slots per CTA: start, A done, bar1 done, B done, bar2 done, C done
 };
 
 }  // namespace
@@ -359,6 +361,10 @@ __device__ __forceinline__ void op_end(const CommDev& c, uint32_t seq0) {
   }
 }
 
+__device__ __forceinline__ void trace_stamp(const CommDev& c, int slot) {
+  if (c.trace != nullptr && threadIdx.x == 0) c.trace[blockIdx.x * 8 + slot] = globaltimer_ns();
+}
+
 template <int W>
 struct Unroll {  // vecs per thread per loop trip, chosen so ~8 wire vecs are in flight per thread
   static constexpr int kU = (W >= 8) ? 1 : (W >= 4 ? 2 : (W >= 2 ? 4 : 8));
@@ -410,6 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long V = (n + 7) / 8;
   const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
   const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  trace_stamp(c, 0);
 
   // phase A: compress my message once, push it into recv[rank] of every rank (mine included)
   for (unsigned long long v0 = first; v0 < V; v0 += stride * U) {
@@ -430,7 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  trace_stamp(c, 1);
   cta_xbar(c, seq0 * 4u + 1u);
+  trace_stamp(c, 2);
 
   // phase B: reduce the W messages (all local now) in rank order, write the caller's tensor
   const uint8_t* mine = c.peer[0] + stage;
@@ -455,6 +464,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  trace_stamp(c, 3);
   op_end(c, seq0);
 }
 
@@ -481,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
   const unsigned long long my_recv = stage + c.rank * c.slice_cap;
   const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;
+  trace_stamp(c, 0);
 
   // ---- phase A -------------------------------------------------------------------------------
   for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
@@ -507,7 +518,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  trace_stamp(c, 1);
   cta_xbar(c, seq0 * 4u + 1u);
+  trace_stamp(c, 2);
 
   // ---- phase B -------------------------------------------------------------------------------
   {
@@ -536,7 +549,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  trace_stamp(c, 3);
   cta_xbar(c, seq0 * 4u + 2u);
+  trace_stamp(c, 4);
 
   // ---- phase C -------------------------------------------------------------------------------
   for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
@@ -562,6 +577,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   }
+  trace_stamp(c, 5);
   op_end(c, seq0);
 }
 
@@ -680,9 +696,10 @@ struct b2_comm {
   size_t arena_bytes = 0;
   size_t stage_bytes = 0;
   uint32_t* counters = nullptr;  // cudaMalloc'ed: opseq, done
+  unsigned long long* trace_dev = nullptr;  // cudaMalloc'ed on demand: kMaxCtas * 8 stamps
   uint32_t* status_host = nullptr;
   int max_ctas = 0;              // 0 = heuristic
-  size_t oneshot_max_wire_bytes = 256 << 10;
+  size_t oneshot_max_wire_bytes = 0;  // 0 = per-world default (see default_oneshot_max); B2_ONESHOT_MAX_BYTES overrides
   uint64_t launches = 0;
   ShmBlock* shm = nullptr;
   std::string shm_path;
@@ -696,6 +713,15 @@ size_t env_size(const char* name, size_t dflt) {
   char* end = nullptr;
   unsigned long long v = strtoull(s, &end, 10);
   return end == s ? dflt : static_cast<size_t>(v);
+}
+
+// Largest message (in wire bytes) for which one-shot beats two-shot, from the measured sweeps in profiles/
+// (8xB200 NVSwitch): one-shot moves (W-1)x the payload per rank but needs one barrier instead of two, so the
+// crossover falls quickly with W.  At W=2 both move the same bytes and one-shot wins until HBM traffic dominates.
+size_t default_oneshot_max(int world) {
+  if (world <= 2) return 16u << 20;
+  if (world <= 4) return 2u << 20;
+  return 512u << 10;
 }
 
 // Arena layout for a given world size; fills d.stage_off / d.slice_cap.
@@ -719,7 +745,7 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
   layout(c, world, stage_bytes);
   c->d.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
-  c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", c->oneshot_max_wire_bytes);
+  c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
   B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
@@ -745,6 +771,8 @@ void free_rank_resources(b2_comm* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->arena) cudaFree(c->arena);
   if (c->counters) cudaFree(c->counters);
+  if (c->trace_dev) cudaFree(c->trace_dev);
+  c->trace_dev = nullptr;
   if (c->status_host) cudaFreeHost(c->status_host);
   c->arena = nullptr;
   c->counters = nullptr;
@@ -1043,6 +1071,21 @@ int b2_comm_status(const b2_comm_t* c) {
 }
 
 uint64_t b2_comm_launch_count(const b2_comm_t* c) { return c ? c->launches : 0; }
+
+int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
+  if (!c) return fail(B2_EINVAL, "null communicator");
+  DeviceGuard g(c->device);
+  if (enable && !c->trace_dev) {
+    B2_CUDA(cudaMalloc(&c->trace_dev, sizeof(unsigned long long) * kMaxCtas * 8));
+    B2_CUDA(cudaMemset(c->trace_dev, 0, sizeof(unsigned long long) * kMaxCtas * 8));
+  }
+  if (out && max_ctas > 0 && c->trace_dev) {
+    const int n = max_ctas < kMaxCtas ? max_ctas : kMaxCtas;
+    B2_CUDA(cudaMemcpy(out, c->trace_dev, sizeof(unsigned long long) * n * 8, cudaMemcpyDeviceToHost));
+  }
+  c->d.trace = enable ? c->trace_dev : nullptr;
+  return B2_OK;
+}
 
 int b2_local_pass(void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
   if (n_elems == 0) return B2_OK;

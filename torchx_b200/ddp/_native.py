@@ -60,6 +60,7 @@ SYMBOLS = [
     "b2_comm_set_max_ctas",
     "b2_comm_status",
     "b2_comm_launch_count",
+    "b2_comm_trace",
     "b2_allreduce",
     "b2_broadcast",
     "b2_barrier",
@@ -122,6 +123,8 @@ def lib() -> ctypes.CDLL:
     L.b2_comm_set_max_ctas.argtypes = [vp, i]
     L.b2_comm_launch_count.restype = u64
     L.b2_comm_launch_count.argtypes = [vp]
+    L.b2_comm_trace.restype = i
+    L.b2_comm_trace.argtypes = [vp, i, ctypes.POINTER(u64), i]
     L.b2_allreduce.restype = i
     L.b2_allreduce.argtypes = [vp, vp, sz, i, f, i, vp]
     L.b2_broadcast.restype = i

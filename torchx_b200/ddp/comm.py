@@ -118,6 +118,12 @@ class Communicator:
         """Raise if any kernel of this communicator timed out waiting for a peer."""
         N.check(N.lib().b2_comm_status(self._h))
 
+    def trace(self, enable: bool, read_ctas: int = 0):
+        """Phase-boundary timestamps (ns, %globaltimer) of the last collective: list of 8-tuples per CTA."""
+        buf = (ctypes.c_uint64 * (8 * read_ctas))() if read_ctas else None
+        N.check(N.lib().b2_comm_trace(self._h, int(enable), buf, read_ctas))
+        return [tuple(buf[8 * i: 8 * i + 8]) for i in range(read_ctas)] if buf is not None else []
+
     @property
     def launches(self) -> int:
         return int(N.lib().b2_comm_launch_count(self._h))
