@@ -219,11 +219,16 @@ class Trainer:
         sampler = ClockSampler(self.device.index)
         sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        profiled = bool(os.environ.get("BENCH_CUDA_PROFILER"))  # ncu --profile-from-start off: capture the timed region only
+        if profiled:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(steps):
             loss = self.step(x, y)
         e1.record()
         self.barrier()
+        if profiled:
+            torch.cuda.profiler.stop()
         clocks = sampler.stop()
         elapsed = e0.elapsed_time(e1) * 1e-3
         launches = (self.comm.launches - launches0) if self.comm is not None else 0

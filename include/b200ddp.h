@@ -64,6 +64,7 @@ extern "C" {
 #define B2_ALGO_AUTO 0
 #define B2_ALGO_ONESHOT 1 /* push whole message to every peer, one flag barrier, reduce locally   */
 #define B2_ALGO_TWOSHOT 2 /* push-scatter (fused cast) -> reduce own slice -> pull-gather (fused cast) */
+#define B2_ALGO_TWOSHOT_PULL 3 /* compress into own stage -> pull-reduce own slice -> pull-gather: no peer stores */
 
 typedef struct b2_comm b2_comm_t; /* opaque */
 

@@ -97,7 +97,7 @@ def test_local_pass_matches_oracle(mode):
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pull"])
 def test_allreduce_matches_oracle_one_device(world, mode, algo):
     w = World([0] * world)
     try:
@@ -118,6 +118,7 @@ def test_allreduce_auto_and_chunking(world):
         for n in (100, 5000, 70001, (1 << 20) + 17):
             _check_allreduce(w, n, "f32_wire_bf16", "auto", "randn", seed=n)
         _check_allreduce(w, (1 << 19) + 3, "f32", "twoshot", "randn", seed=5)
+        _check_allreduce(w, (1 << 20) + 9, "f32_wire_bf16", "twoshot_pull", "special", seed=6)
     finally:
         w.close()
 
@@ -128,7 +129,7 @@ def test_back_to_back_ops_reuse_staging_safely():
     W = 4
     w = World([0] * W)
     try:
-        plan = [(1000 + 37 * i, "oneshot" if i % 3 == 0 else "twoshot") for i in range(40)]
+        plan = [(1000 + 37 * i, ("oneshot", "twoshot", "twoshot_pull")[i % 3]) for i in range(42)]
         tens = [[None] * len(plan) for _ in range(W)]
         wants = []
         for k, (n, _) in enumerate(plan):
@@ -204,7 +205,7 @@ def test_dead_peer_times_out_instead_of_hanging():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pull"])
 def test_allreduce_across_devices(world, algo, cuda_count):
     """Real NVLink/NVSwitch peers (skipped on a 1-GPU box)."""
     devs = _devices(world, cuda_count, spread=True)

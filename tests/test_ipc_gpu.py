@@ -35,7 +35,7 @@ def _run_world(world, devices, tmp_path, n=100003):
                 p.kill()
     for r, p in enumerate(procs):
         assert p.returncode == 0, f"rank {r} failed:\n{outs[r]}"
-    modes = [oracle.B2O_F32_WIRE_BF16, oracle.B2O_F32_WIRE_BF16, oracle.B2O_F32]
+    modes = [oracle.B2O_F32_WIRE_BF16, oracle.B2O_F32_WIRE_BF16, oracle.B2O_F32, oracle.B2O_F32_WIRE_BF16]
     for r in range(world):
         got = np.load(tmp_path / f"r{r}.npz")
         for k, mode in enumerate(modes):

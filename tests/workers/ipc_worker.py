@@ -29,7 +29,7 @@ def main() -> None:
     comm.set_timeout(30.0)
     comm.set_max_ctas(a.max_ctas)
     results = {}
-    for k, (algo, mode) in enumerate([("twoshot", "bf16"), ("oneshot", "bf16"), ("twoshot", "f32")]):
+    for k, (algo, mode) in enumerate([("twoshot", "bf16"), ("oneshot", "bf16"), ("twoshot", "f32"), ("twoshot_pull", "bf16")]):
         x = make_inputs(a.world, a.n, 10 + k, "special")[a.rank]
         t = torch.from_numpy(x).to(f"cuda:{a.device}")
         comm.allreduce_(t, wire=mode, algo=algo)

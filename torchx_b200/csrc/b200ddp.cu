@@ -63,6 +63,8 @@ struct CommDev {
                                     // unrolled device loops index it with compile-time constants (registers,
                                     // not a local-memory copy of the parameter block) and so the W ranks
                                     // never all target the same peer in the same loop step.
+  uint8_t* abs[B2_MAX_WORLD];       // abs[r] = rank r's arena (absolute order): used where values must be combined
+                                    // in rank order, so the loop index is both the pointer index and the rank
   uint32_t* opseq;                  // local: number of collectives completed on this communicator
   uint32_t* done;                   // local: CTAs of the running collective that reached the epilogue
   uint32_t* status;                 // host-mapped: 0 = healthy, else a B2_E* code (positive)
@@ -581,6 +583,116 @@ __global__ void __launch_bounds__(kThreads, 1)
   op_end(c, seq0);
 }
 
+// Two-shot, pull-pull variant.  Measured on 8xB200 (profiles/r01_phase_trace_w4.md): remote LOADS stream at the full
+// NVLink rate (~780 GB/s per GPU) while the push-scatter of k_twoshot only reaches ~440 GB/s once the release fence has
+// drained its stores, and a barrier that follows purely LOCAL stores costs ~3 us instead of 7-17 us.  So here nothing is
+// ever stored to a peer except flags:
+//   A0 compress : read my bucket once, cast+scale, store ALL W slices into MY OWN stage (L2-resident for DDP bucket sizes)
+//   B  pull-reduce : LOAD slice `me` from every rank's stage (rank order), fp32 accumulate, round once -> my "reduced"
+//   C  pull-gather : as in k_twoshot
+// The separate local reduce pass disappears (it is fused into the loads of B).
+template <int MODE, int W>
+__global__ void __launch_bounds__(kThreads, 1)
+    k_twoshot_pull(CommDev c, void* buf, unsigned long long n, float scale) {
+  using namespace dev;
+  constexpr int WVB = Wire<MODE>::kBytes;
+  constexpr int U = Unroll<W>::kU;
+  const uint32_t seq0 = op_begin(c);
+  const unsigned long long stage = (seq0 & 1u) ? c.stage_off[1] : c.stage_off[0];
+  const bool aligned = buf_aligned<MODE>(buf);
+  const unsigned long long V = (n + 7) / 8;
+  const unsigned long long Ls = (V + W - 1) / W;
+  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
+  const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
+  const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;
+  uint8_t* mine = c.peer[0];
+  trace_stamp(c, 0);
+
+  // ---- phase A0: region j of my stage <- my compressed slice j ------------------------------------
+  for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+    F8 x[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) x[u][j] = load_in<MODE>(buf, gv * 8, n, aligned);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V)
+          st_wire<MODE>(mine + stage + j * c.slice_cap + v * WVB, compress<MODE>(x[u][j], scale));
+      }
+    }
+  }
+  trace_stamp(c, 1);
+  cta_xbar(c, seq0 * 4u + 1u);
+  trace_stamp(c, 2);
+
+  // ---- phase B: pull my slice from every rank, reduce in rank order --------------------------------
+  {
+    const unsigned long long base = c.rank * Ls;
+    const unsigned long long my_region = stage + c.rank * c.slice_cap;
+    for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+      Wire<MODE> w[U][W];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long v = v0 + u * stride;
+        if (v < Ls && base + v < V) {
+#pragma unroll
+          for (int r = 0; r < W; ++r) w[u][r] = ld_wire<MODE>(c.abs[r] + my_region + v * WVB);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned long long v = v0 + u * stride;
+        if (v < Ls && base + v < V) {
+          F8 s = widen<MODE>(w[u][0]);
+#pragma unroll
+          for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));
+          st_wire<MODE>(mine + reduced + v * WVB, finalize<MODE>(s));
+        }
+      }
+    }
+  }
+  trace_stamp(c, 3);
+  cta_xbar(c, seq0 * 4u + 2u);
+  trace_stamp(c, 4);
+
+  // ---- phase C: pull-gather ---------------------------------------------------------------------
+  for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
+    Wire<MODE> w[U][W];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) w[u][jj] = ld_wire<MODE>(c.peer[jj] + reduced + v * WVB);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const unsigned long long v = v0 + u * stride;
+#pragma unroll
+      for (int jj = 0; jj < W; ++jj) {
+        const int j = (c.rank + jj) % W;
+        const unsigned long long gv = j * Ls + v;
+        if (v < Ls && gv < V) store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
+      }
+    }
+  }
+  trace_stamp(c, 5);
+  op_end(c, seq0);
+}
+
 // Broadcast of raw bytes: root pushes into every peer's stage, one barrier, peers copy out.
 __global__ void __launch_bounds__(kThreads, 1)
     k_broadcast(CommDev c, uint8_t* buf, unsigned long long bytes, int root) {
@@ -699,6 +811,7 @@ struct b2_comm {
   unsigned long long* trace_dev = nullptr;  // cudaMalloc'ed on demand: kMaxCtas * 8 stamps
   uint32_t* status_host = nullptr;
   int max_ctas = 0;              // 0 = heuristic
+  int auto_twoshot = B2_ALGO_TWOSHOT;  // which two-shot AUTO uses (B2_AUTO_TWOSHOT=2|3 overrides)
   size_t oneshot_max_wire_bytes = 0;  // 0 = per-world default (see default_oneshot_max); B2_ONESHOT_MAX_BYTES overrides
   uint64_t launches = 0;
   ShmBlock* shm = nullptr;
@@ -746,6 +859,7 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
   c->d.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
+  c->auto_twoshot = env_size("B2_AUTO_TWOSHOT", B2_ALGO_TWOSHOT) == B2_ALGO_TWOSHOT_PULL ? B2_ALGO_TWOSHOT_PULL : B2_ALGO_TWOSHOT;
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
   B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
@@ -764,7 +878,10 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
 }
 
 void rotate_peers(b2_comm* c) {
-  for (int jj = 0; jj < c->d.world; ++jj) c->d.peer[jj] = c->arena_of[(c->d.rank + jj) % c->d.world];
+  for (int jj = 0; jj < c->d.world; ++jj) {
+    c->d.peer[jj] = c->arena_of[(c->d.rank + jj) % c->d.world];
+    c->d.abs[jj] = c->arena_of[jj];
+  }
 }
 
 void free_rank_resources(b2_comm* c) {
@@ -810,13 +927,22 @@ cudaError_t launch_twoshot(const b2_comm* c, int grid, void* buf, unsigned long 
   return cudaGetLastError();
 }
 
+template <int MODE, int W>
+cudaError_t launch_twoshot_pull(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+                                cudaStream_t s) {
+  k_twoshot_pull<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  return cudaGetLastError();
+}
+
+// kind: 1 = one-shot, 2 = two-shot (push-scatter), 3 = two-shot (pull-pull)
 template <int MODE>
-cudaError_t launch_by_world(const b2_comm* c, bool oneshot, int grid, void* buf, unsigned long long n,
+cudaError_t launch_by_world(const b2_comm* c, int kind, int grid, void* buf, unsigned long long n,
                             float scale, cudaStream_t s) {
 #define B2_CASE(Wv)                                                                    \
   case Wv:                                                                             \
-    return oneshot ? launch_oneshot<MODE, Wv>(c, grid, buf, n, scale, s)               \
-                   : launch_twoshot<MODE, Wv>(c, grid, buf, n, scale, s);
+    return kind == 1   ? launch_oneshot<MODE, Wv>(c, grid, buf, n, scale, s)           \
+           : kind == 2 ? launch_twoshot<MODE, Wv>(c, grid, buf, n, scale, s)           \
+                       : launch_twoshot_pull<MODE, Wv>(c, grid, buf, n, scale, s);
   switch (c->d.world) {
     B2_CASE(2)
     B2_CASE(3)
@@ -1075,14 +1201,12 @@ uint64_t b2_comm_launch_count(const b2_comm_t* c) { return c ? c->launches : 0; 
 int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
   if (!c) return fail(B2_EINVAL, "null communicator");
   DeviceGuard g(c->device);
-  if (enable && !c->trace_dev) {
-    B2_CUDA(cudaMalloc(&c->trace_dev, sizeof(unsigned long long) * kMaxCtas * 8));
-    B2_CUDA(cudaMemset(c->trace_dev, 0, sizeof(unsigned long long) * kMaxCtas * 8));
-  }
+  if (enable && !c->trace_dev) B2_CUDA(cudaMalloc(&c->trace_dev, sizeof(unsigned long long) * kMaxCtas * 8));
   if (out && max_ctas > 0 && c->trace_dev) {
     const int n = max_ctas < kMaxCtas ? max_ctas : kMaxCtas;
     B2_CUDA(cudaMemcpy(out, c->trace_dev, sizeof(unsigned long long) * n * 8, cudaMemcpyDeviceToHost));
   }
+  if (enable) B2_CUDA(cudaMemset(c->trace_dev, 0, sizeof(unsigned long long) * kMaxCtas * 8));  // no stale CTAs
   c->d.trace = enable ? c->trace_dev : nullptr;
   return B2_OK;
 }
@@ -1114,7 +1238,7 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
   if (!c) return fail(B2_EINVAL, "null communicator");
   if (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16)
     return fail(B2_EINVAL, "unknown mode %d", mode);
-  if (algo != B2_ALGO_AUTO && algo != B2_ALGO_ONESHOT && algo != B2_ALGO_TWOSHOT)
+  if (algo != B2_ALGO_AUTO && algo != B2_ALGO_ONESHOT && algo != B2_ALGO_TWOSHOT && algo != B2_ALGO_TWOSHOT_PULL)
     return fail(B2_EINVAL, "unknown algo %d", algo);
   if (n_elems == 0) return B2_OK;
   if (!buf) return fail(B2_EINVAL, "b2_allreduce: null buffer");
@@ -1136,14 +1260,13 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
   size_t left = n_elems;
   while (left > 0) {
     const unsigned long long V_left = (left + 7) / 8;
-    bool oneshot;
-    if (algo == B2_ALGO_ONESHOT) {
-      oneshot = true;
-    } else if (algo == B2_ALGO_TWOSHOT) {
-      oneshot = false;
+    int kind;
+    if (algo == B2_ALGO_AUTO) {
+      kind = (V_left * wvb <= c->oneshot_max_wire_bytes && V_left <= cap_vecs) ? B2_ALGO_ONESHOT : c->auto_twoshot;
     } else {
-      oneshot = V_left * wvb <= c->oneshot_max_wire_bytes && V_left <= cap_vecs;
+      kind = algo;
     }
+    const bool oneshot = kind == B2_ALGO_ONESHOT;
     const unsigned long long max_vecs = oneshot ? cap_vecs : cap_vecs * W;
     const unsigned long long V = V_left < max_vecs ? V_left : max_vecs;
     const size_t n = V == V_left ? left : static_cast<size_t>(V) * 8;
@@ -1152,13 +1275,13 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
     cudaError_t e;
     switch (mode) {
       case B2_F32_WIRE_BF16:
-        e = launch_by_world<B2_F32_WIRE_BF16>(c, oneshot, grid, p, n, scale, s);
+        e = launch_by_world<B2_F32_WIRE_BF16>(c, kind, grid, p, n, scale, s);
         break;
       case B2_F32:
-        e = launch_by_world<B2_F32>(c, oneshot, grid, p, n, scale, s);
+        e = launch_by_world<B2_F32>(c, kind, grid, p, n, scale, s);
         break;
       default:
-        e = launch_by_world<B2_BF16>(c, oneshot, grid, p, n, scale, s);
+        e = launch_by_world<B2_BF16>(c, kind, grid, p, n, scale, s);
         break;
     }
     if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));

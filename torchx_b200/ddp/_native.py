@@ -34,6 +34,7 @@ B2_BF16 = 2
 B2_ALGO_AUTO = 0
 B2_ALGO_ONESHOT = 1
 B2_ALGO_TWOSHOT = 2
+B2_ALGO_TWOSHOT_PULL = 3
 
 NVCC_FLAGS = [
     "-gencode",

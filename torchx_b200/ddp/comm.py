@@ -20,7 +20,7 @@ _MODE_FOR = {
     ("f32", "f32"): N.B2_F32,
     ("bf16", "bf16"): N.B2_BF16,
 }
-ALGOS = {"auto": N.B2_ALGO_AUTO, "oneshot": N.B2_ALGO_ONESHOT, "twoshot": N.B2_ALGO_TWOSHOT}
+ALGOS = {"auto": N.B2_ALGO_AUTO, "oneshot": N.B2_ALGO_ONESHOT, "twoshot": N.B2_ALGO_TWOSHOT, "twoshot_pull": N.B2_ALGO_TWOSHOT_PULL}
 
 
 def mode_for(tensor: torch.Tensor, wire: str = "bf16") -> int:
