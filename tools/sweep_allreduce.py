@@ -103,8 +103,9 @@ def main():
                     stamps = [st for st in comm.trace(False, read_ctas=296) if st[0]]
                     if stamps:
                         t0 = min(st[0] for st in stamps)
-                        last = 5 if algo == "twoshot" else 3
-                        names = ["scatter", "bar1", "reduce", "bar2", "gather"] if algo == "twoshot" else ["push", "bar1", "reduce"]
+                        last = 3 if algo == "oneshot" else 5
+                        names = {"oneshot": ["push", "bar1", "reduce"], "twoshot": ["scatter", "bar1", "reduce", "bar2", "gather"],
+                                 "twoshot_pull": ["compress", "bar1", "pull_reduce", "bar2", "gather"]}[algo]
                         med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
                         row[key]["trace_us"] = {
                             "ctas": len(stamps), "start_spread": round((max(st[0] for st in stamps) - t0) / 1e3, 2),

@@ -95,6 +95,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -329,7 +335,8 @@ __device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
     st_release_sys(theirs, seq);
     unsigned long long t0 = 0;
     unsigned spins = 0;
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - seq) < 0) {
+    // poll with a relaxed load (no fence per iteration); ONE acquire fence after the flag has been seen
+    while (static_cast<int32_t>(ld_relaxed_sys(mine) - seq) < 0) {
       if ((++spins & 63u) == 0) {
         const unsigned long long now = globaltimer_ns();
         if (t0 == 0) {
@@ -341,6 +348,7 @@ __device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
         }
       }
     }
+    fence_acq_rel_sys();
   }
   __syncthreads();  // peers' data is now visible to every thread of this CTA
 }
