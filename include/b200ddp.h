@@ -80,7 +80,7 @@ const char* b2_last_error(void);
  * through the B2_SHM_NAME environment variable) and the same `epoch` (the launcher's restart
  * counter: a re-launched gang uses a new epoch so survivors never map a dead peer's memory).
  * `device` is the CUDA ordinal this rank is pinned to.  `stage_bytes` is the per-rank size of ONE
- * of the two symmetric staging buffers (0 = default 128 MiB); messages larger than what fits are
+ * of the two symmetric staging buffers (0 = default 512 MiB); messages larger than what fits are
  * chunked internally.  `timeout_ms` bounds the rendezvous (0 = default 120 s).
  */
 int b2_comm_create(b2_comm_t** out, int rank, int world, int device, const char* shm_name,

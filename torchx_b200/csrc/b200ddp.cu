@@ -48,7 +48,7 @@ constexpr int kThreads = 512;                // threads per CTA for every kernel
 constexpr int kMaxCtas = 296;                // 2 x 148 SMs: upper bound on the grid of a collective
 constexpr int kFlagSlotBytes = 32;           // one 32 B sector of flags per CTA index (8 x u32, one per peer)
 constexpr size_t kFlagRegionBytes = 64 << 10;  // >= kMaxCtas * kFlagSlotBytes, keeps stages 64 KiB aligned
-constexpr size_t kDefaultStageBytes = 128ull << 20;
+constexpr size_t kDefaultStageBytes = 512ull << 20;  // x2 stages = 1 GiB of the 180 GB: a 1 GiB fp32 bucket is one launch
 constexpr unsigned long long kDefaultTimeoutNs = 30ull * 1000ull * 1000ull * 1000ull;
 
 static_assert(kMaxCtas * kFlagSlotBytes <= (int)kFlagRegionBytes, "flag region too small");
@@ -410,6 +410,149 @@ __global__ void __launch_bounds__(kThreads) k_local_pass(void* buf, unsigned lon
         store_out<MODE>(buf, v * 8, n, aligned, finalize<MODE>(widen<MODE>(c)));
       }
     }
+  }
+}
+
+// ---- TMA-staged variant of the local pass --------------------------------------------------------------------
+// Persistent CTAs stream 16 KiB tiles through a 4-deep shared-memory ring: one elected thread issues
+// cp.async.bulk (global -> shared, completion on an mbarrier; SASS UBLKCP), all threads round the tile in place in
+// shared memory, and the tile goes back with a bulk store (shared -> global, bulk_group).  Loads of the next tiles are
+// always in flight while the current tile is being rounded and stored, with no registers tied up by outstanding
+// loads - 64 KiB of HBM reads in flight per CTA from a single issuing thread.
+namespace tma {
+
+constexpr int kTileBytes = 16 << 10;
+constexpr int kStages = 4;
+constexpr int kTmaThreads = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+// x <- round(wire(scale * x)) on one 16-byte group (4 fp32 or 8 bf16), same arithmetic as compress+finalize.
+template <int MODE>
+__device__ __forceinline__ uint4 round16(uint4 q, float scale) {
+  using namespace dev;
+  if constexpr (MODE == B2_BF16) {
+    uint32_t in[4] = {q.x, q.y, q.z, q.w}, out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = pack_bf16x2(__fmul_rn(bf16_lo(in[i]), scale), __fmul_rn(bf16_hi(in[i]), scale));
+    return make_uint4(out[0], out[1], out[2], out[3]);
+  } else {
+    float f[4] = {__uint_as_float(q.x), __uint_as_float(q.y), __uint_as_float(q.z), __uint_as_float(q.w)};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i += 2) {
+      if constexpr (MODE == B2_F32) {
+        o[i] = __float_as_uint(__fmul_rn(f[i], scale));
+        o[i + 1] = __float_as_uint(__fmul_rn(f[i + 1], scale));
+      } else {
+        const uint32_t p = pack_bf16x2(f[i], f[i + 1]);                                        // .to(bf16)
+        const uint32_t r = pack_bf16x2(__fmul_rn(bf16_lo(p), scale), __fmul_rn(bf16_hi(p), scale));  // .div_(W), bf16
+        o[i] = r << 16;             // widen back to fp32: bf16 bits in the high half
+        o[i + 1] = r & 0xffff0000u;
+      }
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+}  // namespace tma
+
+template <int MODE>
+__global__ void __launch_bounds__(tma::kTmaThreads) k_local_pass_tma(void* buf, unsigned long long n, float scale) {
+  using namespace tma;
+  extern __shared__ __align__(128) uint8_t ring_raw[];  // kStages * kTileBytes of dynamic shared memory
+  uint8_t(*ring)[kTileBytes] = reinterpret_cast<uint8_t(*)[kTileBytes]>(ring_raw);
+  __shared__ alignas(8) uint64_t full[kStages];
+  constexpr int kElem = MODE == B2_BF16 ? 2 : 4;
+  const unsigned long long bytes = n * kElem;
+  const unsigned long long ntiles = bytes / kTileBytes;  // full tiles go through TMA; the tail is handled below
+  uint8_t* base = static_cast<uint8_t*>(buf);
+  const unsigned long long my_first = blockIdx.x;
+  const unsigned long long step = gridDim.x;
+  const unsigned long long my_count = my_first < ntiles ? (ntiles - my_first + step - 1) / step : 0;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      if (static_cast<unsigned long long>(s) < my_count) {
+        mbar_arrive_expect_tx(&full[s], kTileBytes);
+        bulk_g2s(ring[s], base + (my_first + s * step) * kTileBytes, kTileBytes, &full[s]);
+      }
+    }
+  }
+  for (unsigned long long k = 0; k < my_count; ++k) {
+    const int s = static_cast<int>(k % kStages);
+    mbar_wait(&full[s], static_cast<uint32_t>((k / kStages) & 1));
+    uint4* tile = reinterpret_cast<uint4*>(ring[s]);
+#pragma unroll
+    for (int i = 0; i < kTileBytes / 16 / kTmaThreads; ++i) {
+      const int idx = i * kTmaThreads + threadIdx.x;  // conflict-free: consecutive lanes, consecutive 16 B
+      tile[idx] = round16<MODE>(tile[idx], scale);
+    }
+    fence_proxy_async();  // my generic-proxy writes to the tile are visible to the bulk store (async proxy)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      bulk_s2g(base + (my_first + k * step) * kTileBytes, ring[s], kTileBytes);
+      bulk_commit();
+      // Refill the stage whose store was issued ONE iteration ago: allowing one group in flight means that older
+      // store has finished reading shared memory, while the store just issued keeps draining.
+      if (k >= 1 && k - 1 + kStages < my_count) {
+        bulk_wait_read<1>();
+        const int sp = static_cast<int>((k - 1) % kStages);
+        mbar_arrive_expect_tx(&full[sp], kTileBytes);
+        bulk_g2s(ring[sp], base + (my_first + (k - 1 + kStages) * step) * kTileBytes, kTileBytes, &full[sp]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_read<0>();  // shared memory must outlive the last store's reads
+  // tail (< 16 KiB): plain loads/stores, spread over the grid
+  const unsigned long long tail0 = ntiles * kTileBytes / kElem;
+  for (unsigned long long e = tail0 + (static_cast<unsigned long long>(blockIdx.x) * kTmaThreads + threadIdx.x) * 8; e < n;
+       e += static_cast<unsigned long long>(gridDim.x) * kTmaThreads * 8) {
+    const dev::F8 x = dev::load_in<MODE>(buf, e, n, false);
+    const dev::Wire<MODE> c = dev::compress<MODE>(x, scale);
+    dev::store_out<MODE>(buf, e, n, false, dev::finalize<MODE>(dev::widen<MODE>(c)));
   }
 }
 
@@ -907,7 +1050,10 @@ void free_rank_resources(b2_comm* c) {
 int grid_for(const b2_comm* c, unsigned long long vecs_per_cta_dim, int unroll) {
   // Enough CTAs that each thread has work, capped so the collective leaves SMs to the backward
   // pass it overlaps with.  Deterministic in (n, world, max_ctas) => identical on every rank.
-  const int cap = c->max_ctas > 0 ? (c->max_ctas > kMaxCtas ? kMaxCtas : c->max_ctas) : 64;
+  // Default cap: 64 CTAs (DDP-bucket sizes: within 3 % of the 128-CTA rate in profiles/r01_sweep_w8.jsonl while
+  // occupying under half of the 148 SMs); 128 once a CTA would otherwise loop more than ~32 times (>= ~128 MiB buckets).
+  const int dflt = vecs_per_cta_dim > 64ull * kThreads * 32ull ? 128 : 64;
+  const int cap = c->max_ctas > 0 ? (c->max_ctas > kMaxCtas ? kMaxCtas : c->max_ctas) : dflt;
   unsigned long long per = static_cast<unsigned long long>(kThreads) * unroll;
   unsigned long long g = (vecs_per_cta_dim + per - 1) / per;
   if (g < 1) g = 1;
@@ -967,6 +1113,24 @@ cudaError_t launch_by_world(const b2_comm* c, int kind, int grid, void* buf, uns
 
 template <int MODE>
 cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStream_t s) {
+  // TMA-staged path for 16 B-aligned buckets of at least 1 MiB (B2_LOCAL_TMA=0 forces the plain ld/st kernel)
+  static const bool use_tma = env_size("B2_LOCAL_TMA", 1) != 0;
+  const unsigned long long nbytes = n * (MODE == B2_BF16 ? 2 : 4);
+  if (use_tma && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20)) {
+    const unsigned long long ntiles = nbytes / tma::kTileBytes;
+    unsigned long long g = ntiles < 148ull * 2 ? ntiles : 148ull * 2;  // persistent: 2 CTAs (2 x 64 KiB rings) per SM
+    constexpr int kSmem = tma::kStages * tma::kTileBytes;
+    static std::atomic<unsigned> configured{0};  // bit d: the 64 KiB opt-in has been set on device d
+    int devno = 0;
+    cudaGetDevice(&devno);
+    if (!(configured.load(std::memory_order_relaxed) & (1u << (devno & 31)))) {
+      const cudaError_t attr = cudaFuncSetAttribute(k_local_pass_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+      if (attr != cudaSuccess) return attr;
+      configured.fetch_or(1u << (devno & 31), std::memory_order_relaxed);
+    }
+    k_local_pass_tma<MODE><<<static_cast<int>(g), tma::kTmaThreads, kSmem, s>>>(buf, n, scale);
+    return cudaGetLastError();
+  }
   const unsigned long long V = (n + 7) / 8;
   unsigned long long g = (V + kThreads * 4ull - 1) / (kThreads * 4ull);
   if (g < 1) g = 1;

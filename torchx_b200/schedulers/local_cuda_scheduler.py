@@ -78,7 +78,7 @@ class CudaOpts(Opts):
     """OMP_NUM_THREADS for workers that do not set it (torchrun's default is 1)."""
 
     stage_mb: int = 0
-    """Per-rank staging buffer size in MiB for the peer-buffer allreduce (0 = library default 128)."""
+    """Per-rank staging buffer size in MiB for the peer-buffer allreduce (0 = library default 512)."""
 
     master_port: int = 0
     """MASTER_PORT handed to the workers (0 = pick a free port at launch)."""
