@@ -4,6 +4,8 @@ import sys
 # In-process multi-rank topologies run W spinning kernels concurrently on W streams; the default of 8
 # hardware work queues would alias two streams onto one queue at W = 8 and serialise them.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Exercise the TMA-staged local pass at test sizes too (the library only defaults to it from 256 MiB up).
+os.environ.setdefault("B2_LOCAL_TMA_MIN_MB", "0")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

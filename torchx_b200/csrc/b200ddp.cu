@@ -1113,10 +1113,14 @@ cudaError_t launch_by_world(const b2_comm* c, int kind, int grid, void* buf, uns
 
 template <int MODE>
 cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStream_t s) {
-  // TMA-staged path for 16 B-aligned buckets of at least 1 MiB (B2_LOCAL_TMA=0 forces the plain ld/st kernel)
+  // TMA-staged path for 16 B-aligned buckets.  Measured on B200 (profiles/r01_local_pass_tma_vs_plain.jsonl): the ring
+  // needs several tiles per CTA to pay for its prologue - slower than the plain kernel below 25 MiB, equal to 168 MiB,
+  // ahead from 512 MiB - so it is the default from 256 MiB up.  B2_LOCAL_TMA_MIN_MB moves the threshold (0 = always
+  // for >= 1 MiB, e.g. for the parity tests), B2_LOCAL_TMA=0 disables it.
   static const bool use_tma = env_size("B2_LOCAL_TMA", 1) != 0;
+  static const unsigned long long tma_min = env_size("B2_LOCAL_TMA_MIN_MB", 256) << 20;
   const unsigned long long nbytes = n * (MODE == B2_BF16 ? 2 : 4);
-  if (use_tma && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20)) {
+  if (use_tma && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20) && nbytes >= tma_min) {
     const unsigned long long ntiles = nbytes / tma::kTileBytes;
     unsigned long long g = ntiles < 148ull * 2 ? ntiles : 148ull * 2;  // persistent: 2 CTAs (2 x 64 KiB rings) per SM
     constexpr int kSmem = tma::kStages * tma::kTileBytes;
