@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--wire", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", default=True, help="(N>1) also report allreduce bus GB/s at the model's bucket sizes and 256 MiB")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false")
     return ap.parse_args()
 
 
@@ -282,6 +284,47 @@ class Trainer:
         h2d = host[0][0].numel() * host[0][0].element_size() + host[0][1].numel() * host[0][1].element_size()
         return elapsed, h2d, loss_host.element_size(), float(loss_host[-1].item())
 
+    def allreduce_points(self):
+        """Second half of BASELINE.json's metric: allreduce bus GB/s (fraction of 900 GB/s/dir) on this arm's data path, for
+        fp32 buckets of the model's sizes and 256 MiB.  ours: one fused launch (bf16 wire, 1/W).  reference: the
+        bf16_compress_hook sequence (cast, div, ncclAllReduce, copy).  busbw = wire bytes / t * 2(W-1)/W, wire = 2 B/element."""
+        torch = self.torch
+        sizes_mib = [7.82, 25.04, 30.04, 256.0]
+        out = []
+        stream = torch.cuda.Stream(device=self.device)
+        k = 2.0 * (self.world - 1) / self.world
+        for mib in sizes_mib:
+            n = int(mib * (1 << 20) / 4) // 8 * 8
+            bufs = [torch.randn(n, device=self.device) for _ in range(2 if mib >= 64 else 6)]
+            iters, warm = (20, 5) if mib >= 64 else (100, 20)
+            if self.comm is not None:
+                def op(b):
+                    self.comm.allreduce_(b, stream=stream)
+            else:
+                import torch.distributed as dist
+
+                def op(b):
+                    c = b.to(torch.bfloat16).div_(self.world)
+                    dist.all_reduce(c)
+                    b.copy_(c)
+            with torch.cuda.stream(stream):
+                for i in range(warm):
+                    op(bufs[i % len(bufs)])
+            stream.synchronize()
+            self.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                for i in range(iters):
+                    op(bufs[i % len(bufs)])
+                e1.record(stream)
+            stream.synchronize()
+            t = self.max_over_ranks(e0.elapsed_time(e1) * 1e-3 / iters)
+            out.append({"bucket_mib_fp32": mib, "us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1),
+                        "frac_of_900": round(2 * n / t * k / 1e9 / 900.0, 4)})
+            del bufs
+        return out
+
     def close(self):
         if self.comm is not None:
             self.comm.close()
@@ -389,6 +432,16 @@ def main():
             k = 2.0 * (world - 1) / world
             line["roofline"]["nvlink_busbw_gbs"] = round(kernel["alg_bytes"] / 4 / kernel["seconds"] * k / 1e9, 1)
             line["roofline"]["nvlink_frac_of_900"] = round(kernel["alg_bytes"] / 4 / kernel["seconds"] * k / 1e9 / 900.0, 4)
+    if kernel is not None and world == 1:
+        tpath = os.path.join(ROOT, "profiles", "r01_local_pass_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))
+            # per launch, like `achieved`: scaled from the profiled 30 MiB launch to this run's mean bucket
+            per_launch = line["roofline"]["alg_bytes_per_launch"]
+            line["roofline"]["traffic"] = int((t["dram_bytes_read"] + t["dram_bytes_write"]) * per_launch / t["alg_bytes"])
+            line["roofline"]["traffic_source"] = t["source"] + "; " + t["note"]
+    if args.sweep and world > 1:
+        line["allreduce"] = tr.allreduce_points()
     if args.impl == "reference":
         line["cpu_baseline"] = {"value": line["value"], "unit": "images/sec", "cores": os.cpu_count(), "kind": "reference",
                                 "sample": "stock torch DistributedDataParallel + NCCL (bf16_compress_hook) - the path `torchx run -s local_cwd dist.ddp` "

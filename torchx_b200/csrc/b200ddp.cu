@@ -1050,9 +1050,9 @@ void free_rank_resources(b2_comm* c) {
 int grid_for(const b2_comm* c, unsigned long long vecs_per_cta_dim, int unroll) {
   // Enough CTAs that each thread has work, capped so the collective leaves SMs to the backward
   // pass it overlaps with.  Deterministic in (n, world, max_ctas) => identical on every rank.
-  // Default cap: 64 CTAs (DDP-bucket sizes: within 3 % of the 128-CTA rate in profiles/r01_sweep_w8.jsonl while
-  // occupying under half of the 148 SMs); 128 once a CTA would otherwise loop more than ~32 times (>= ~128 MiB buckets).
-  const int dflt = vecs_per_cta_dim > 64ull * kThreads * 32ull ? 128 : 64;
+  // Default cap: 64 CTAs; 128 once 64 CTAs would each loop more than twice (from ~16 MiB fp32 buckets at W=8), where the
+  // sweeps in profiles/r01_sweep_w*.jsonl show the 128-CTA grid 3-6 % faster.  One CTA per SM (512 threads, <= 128 regs).
+  const int dflt = vecs_per_cta_dim > 64ull * kThreads * static_cast<unsigned long long>(unroll) * 2ull ? 128 : 64;
   const int cap = c->max_ctas > 0 ? (c->max_ctas > kMaxCtas ? kMaxCtas : c->max_ctas) : dflt;
   unsigned long long per = static_cast<unsigned long long>(kThreads) * unroll;
   unsigned long long g = (vecs_per_cta_dim + per - 1) / per;
