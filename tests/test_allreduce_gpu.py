@@ -33,8 +33,8 @@ class World:
         same_device = len(set(devices)) == 1
         for c in self.comms:
             c.set_timeout(timeout_s)
-            if same_device:  # all W kernels must be co-resident on one GPU: W * grid <= #SMs
-                c.set_max_ctas(max(1, 128 // len(devices)))
+            if same_device:  # all kernels must be co-resident on one GPU: W ranks x 2 lanes x grid <= #SMs (1 CTA per SM)
+                c.set_max_ctas(max(1, 64 // len(devices)))
 
     def run(self, fn):
         """fn(rank, comm, stream) launches that rank's work; then wait for all and check health."""
@@ -119,6 +119,22 @@ def test_allreduce_auto_and_chunking(world):
             _check_allreduce(w, n, "f32_wire_bf16", "auto", "randn", seed=n)
         _check_allreduce(w, (1 << 19) + 3, "f32", "twoshot", "randn", seed=5)
         _check_allreduce(w, (1 << 20) + 9, "f32_wire_bf16", "twoshot_pull", "special", seed=6)
+    finally:
+        w.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("algo", ["twoshot", "twoshot_pull", "auto"])
+def test_large_buckets_split_over_two_lanes(world, algo):
+    """>= 4 MiB on the wire: the collective runs as two concurrent half-collectives (lane 1 on an internal stream)."""
+    w = World([0] * world, stage_mb=32)
+    try:
+        before = w.comms[0].launches
+        _check_allreduce(w, (1 << 21) + 8 * world + 5, "f32_wire_bf16", algo, "special", seed=21)
+        # AUTO at W=2 still prefers one-shot at this size (one launch); the two-shot algorithms split
+        assert w.comms[0].launches - before == (1 if (algo == "auto" and world == 2) else 2)
+        _check_allreduce(w, (1 << 20) + 3, "f32", "twoshot", "randn", seed=22)  # 4 MiB of fp32 wire: split as well
+        _check_allreduce(w, 3000, "f32_wire_bf16", "twoshot", "randn", seed=23)  # small again: single lane, same comm
     finally:
         w.close()
 

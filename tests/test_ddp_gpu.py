@@ -25,7 +25,7 @@ def _make_world(W, seeds, **kw):
     comms = Communicator.create_local([0] * W, stage_mb=8)
     for c in comms:
         c.set_timeout(20.0)
-        c.set_max_ctas(8)
+        c.set_max_ctas(4)
     # construction broadcasts rank 0's parameters: every rank's constructor must be in flight together, so build
     # them on side streams (the constructor enqueues its broadcast on the current stream)
     streams = [torch.cuda.Stream() for _ in range(W)]

@@ -69,6 +69,7 @@ struct CommDev {
   uint32_t* done;                   // local: CTAs of the running collective that reached the epilogue
   uint32_t* status;                 // host-mapped: 0 = healthy, else a B2_E* code (positive)
   unsigned long long timeout_ns;    // bound on any single peer wait
+  unsigned long long flag_off;      // byte offset of this LANE's flag region inside an arena
   unsigned long long stage_off[2];  // byte offsets of the two staging buffers inside an arena
   unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
                                     //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced"
@@ -329,7 +330,7 @@ __device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
 #pragma unroll
     for (int i = 1; i < B2_MAX_WORLD; ++i)
       if (jj == i) their_arena = c.peer[i];  // select chain: keeps the parameter block out of local memory
-    const size_t slot = static_cast<size_t>(blockIdx.x) * kFlagSlotBytes;
+    const size_t slot = c.flag_off + static_cast<size_t>(blockIdx.x) * kFlagSlotBytes;
     uint32_t* theirs = reinterpret_cast<uint32_t*>(their_arena + slot) + c.rank;
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(c.peer[0] + slot) + p;
     st_release_sys(theirs, seq);
@@ -949,8 +950,19 @@ struct ShmBlock {
 
 }  // namespace
 
+// A communicator has two LANES: fully independent flag regions, stages and op counters inside the same arena.  Every
+// collective runs on lane 0; a large two-shot allreduce is split in two halves that run CONCURRENTLY, lane 1 on an
+// internal stream forked from / joined into the caller's stream, so that the barriers, the local reduce and the launch
+// gap of one half overlap the NVLink phases of the other (profiles/r01_phase_trace_w4.md: ~25 us of a 55 us bucket
+// collective is not wire time).
+constexpr int kLanes = 2;
+
 struct b2_comm {
-  CommDev d{};
+  CommDev d{};        // lane 0
+  CommDev d1{};       // lane 1 (same peers; its own flags / stages / counters)
+  cudaStream_t lane_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  size_t split_min_wire_bytes = 0;  // two-shot messages of at least this many wire bytes are split over the lanes
   int device = -1;
   bool local_world = false;    // created by b2_comm_create_local (no IPC, no shm)
   bool peer_is_ipc[B2_MAX_WORLD] = {};
@@ -993,36 +1005,47 @@ void layout(b2_comm* c, int world, size_t stage_bytes) {
   size_t cap = stage_bytes / (world + 1);
   cap &= ~static_cast<size_t>(255);
   c->stage_bytes = cap * (world + 1);
-  c->d.slice_cap = cap;
-  c->d.stage_off[0] = kFlagRegionBytes;
-  c->d.stage_off[1] = kFlagRegionBytes + c->stage_bytes;
-  c->arena_bytes = kFlagRegionBytes + 2 * c->stage_bytes;
+  const size_t stages0 = kLanes * kFlagRegionBytes;
+  for (int lane = 0; lane < kLanes; ++lane) {
+    CommDev& d = lane == 0 ? c->d : c->d1;
+    d.slice_cap = cap;
+    d.flag_off = lane * kFlagRegionBytes;
+    d.stage_off[0] = stages0 + (2 * lane + 0) * c->stage_bytes;
+    d.stage_off[1] = stages0 + (2 * lane + 1) * c->stage_bytes;
+  }
+  c->arena_bytes = stages0 + 2 * kLanes * c->stage_bytes;
 }
 
 int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   c->device = device;
-  c->d.rank = rank;
-  c->d.world = world;
+  c->d.rank = c->d1.rank = rank;
+  c->d.world = c->d1.world = world;
   if (stage_bytes == 0) stage_bytes = env_size("B2_STAGE_MB", kDefaultStageBytes >> 20) << 20;
   if (stage_bytes < (static_cast<size_t>(world + 1) << 12))
     return fail(B2_EINVAL, "stage_bytes=%zu too small for world=%d", stage_bytes, world);
   layout(c, world, stage_bytes);
-  c->d.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
+  c->d.timeout_ns = c->d1.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
+  c->split_min_wire_bytes = env_size("B2_SPLIT_MIN_BYTES", 4u << 20);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
   c->auto_twoshot = env_size("B2_AUTO_TWOSHOT", B2_ALGO_TWOSHOT) == B2_ALGO_TWOSHOT_PULL ? B2_ALGO_TWOSHOT_PULL : B2_ALGO_TWOSHOT;
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
-  B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
+  B2_CUDA(cudaMemset(c->arena, 0, kLanes * kFlagRegionBytes));
   B2_CUDA(cudaMalloc(&c->counters, 256));
   B2_CUDA(cudaMemset(c->counters, 0, 256));
   c->d.opseq = c->counters;
   c->d.done = c->counters + 32;  // a different 128 B line
+  c->d1.opseq = c->counters + 16;
+  c->d1.done = c->counters + 48;
+  B2_CUDA(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
+  B2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  B2_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   B2_CUDA(cudaHostAlloc(&c->status_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
   memset(c->status_host, 0, 64);
   void* sdev = nullptr;
   B2_CUDA(cudaHostGetDevicePointer(&sdev, c->status_host, 0));
-  c->d.status = static_cast<uint32_t*>(sdev);
+  c->d.status = c->d1.status = static_cast<uint32_t*>(sdev);
   B2_CUDA(cudaDeviceSynchronize());
   c->arena_of[rank] = static_cast<uint8_t*>(c->arena);
   return B2_OK;
@@ -1030,8 +1053,8 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
 
 void rotate_peers(b2_comm* c) {
   for (int jj = 0; jj < c->d.world; ++jj) {
-    c->d.peer[jj] = c->arena_of[(c->d.rank + jj) % c->d.world];
-    c->d.abs[jj] = c->arena_of[jj];
+    c->d.peer[jj] = c->d1.peer[jj] = c->arena_of[(c->d.rank + jj) % c->d.world];
+    c->d.abs[jj] = c->d1.abs[jj] = c->arena_of[jj];
   }
 }
 
@@ -1039,6 +1062,11 @@ void free_rank_resources(b2_comm* c) {
   if (c->device >= 0) cudaSetDevice(c->device);
   if (c->arena) cudaFree(c->arena);
   if (c->counters) cudaFree(c->counters);
+  if (c->lane_stream) cudaStreamDestroy(c->lane_stream);
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
+  c->lane_stream = nullptr;
+  c->ev_fork = c->ev_join = nullptr;
   if (c->trace_dev) cudaFree(c->trace_dev);
   c->trace_dev = nullptr;
   if (c->status_host) cudaFreeHost(c->status_host);
@@ -1069,35 +1097,35 @@ constexpr int unroll_of() {
 int unroll_for_world(int w) { return w >= 8 ? 1 : (w >= 4 ? 2 : (w >= 2 ? 4 : 8)); }
 
 template <int MODE, int W>
-cudaError_t launch_oneshot(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+cudaError_t launch_oneshot(const CommDev& d, int grid, void* buf, unsigned long long n, float scale,
                            cudaStream_t s) {
-  k_oneshot<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  k_oneshot<MODE, W><<<grid, kThreads, 0, s>>>(d, buf, n, scale);
   return cudaGetLastError();
 }
 template <int MODE, int W>
-cudaError_t launch_twoshot(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+cudaError_t launch_twoshot(const CommDev& d, int grid, void* buf, unsigned long long n, float scale,
                            cudaStream_t s) {
-  k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(d, buf, n, scale);
   return cudaGetLastError();
 }
 
 template <int MODE, int W>
-cudaError_t launch_twoshot_pull(const b2_comm* c, int grid, void* buf, unsigned long long n, float scale,
+cudaError_t launch_twoshot_pull(const CommDev& d, int grid, void* buf, unsigned long long n, float scale,
                                 cudaStream_t s) {
-  k_twoshot_pull<MODE, W><<<grid, kThreads, 0, s>>>(c->d, buf, n, scale);
+  k_twoshot_pull<MODE, W><<<grid, kThreads, 0, s>>>(d, buf, n, scale);
   return cudaGetLastError();
 }
 
 // kind: 1 = one-shot, 2 = two-shot (push-scatter), 3 = two-shot (pull-pull)
 template <int MODE>
-cudaError_t launch_by_world(const b2_comm* c, int kind, int grid, void* buf, unsigned long long n,
+cudaError_t launch_by_world(const CommDev& d, int kind, int grid, void* buf, unsigned long long n,
                             float scale, cudaStream_t s) {
 #define B2_CASE(Wv)                                                                    \
   case Wv:                                                                             \
-    return kind == 1   ? launch_oneshot<MODE, Wv>(c, grid, buf, n, scale, s)           \
-           : kind == 2 ? launch_twoshot<MODE, Wv>(c, grid, buf, n, scale, s)           \
-                       : launch_twoshot_pull<MODE, Wv>(c, grid, buf, n, scale, s);
-  switch (c->d.world) {
+    return kind == 1   ? launch_oneshot<MODE, Wv>(d, grid, buf, n, scale, s)           \
+           : kind == 2 ? launch_twoshot<MODE, Wv>(d, grid, buf, n, scale, s)           \
+                       : launch_twoshot_pull<MODE, Wv>(d, grid, buf, n, scale, s);
+  switch (d.world) {
     B2_CASE(2)
     B2_CASE(3)
     B2_CASE(4)
@@ -1141,6 +1169,18 @@ cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStrea
   if (g > 148ull * 4) g = 148ull * 4;  // 4 resident CTAs per SM keep ~64 KiB of loads in flight per SM
   k_local_pass<MODE><<<static_cast<int>(g), kThreads, 0, s>>>(buf, n, scale);
   return cudaGetLastError();
+}
+
+cudaError_t launch_mode(const CommDev& d, int mode, int kind, int grid, void* buf, unsigned long long n, float scale,
+                        cudaStream_t s) {
+  switch (mode) {
+    case B2_F32_WIRE_BF16:
+      return launch_by_world<B2_F32_WIRE_BF16>(d, kind, grid, buf, n, scale, s);
+    case B2_F32:
+      return launch_by_world<B2_F32>(d, kind, grid, buf, n, scale, s);
+    default:
+      return launch_by_world<B2_BF16>(d, kind, grid, buf, n, scale, s);
+  }
 }
 
 size_t elem_bytes(int mode) { return mode == B2_BF16 ? 2 : 4; }
@@ -1354,7 +1394,7 @@ int b2_comm_device(const b2_comm_t* c) { return c ? c->device : B2_EINVAL; }
 
 int b2_comm_set_timeout_ms(b2_comm_t* c, int timeout_ms) {
   if (!c || timeout_ms <= 0) return fail(B2_EINVAL, "b2_comm_set_timeout_ms: bad arguments");
-  c->d.timeout_ns = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
+  c->d.timeout_ns = c->d1.timeout_ns = static_cast<unsigned long long>(timeout_ms) * 1000000ull;
   return B2_OK;
 }
 
@@ -1446,22 +1486,25 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
     const unsigned long long max_vecs = oneshot ? cap_vecs : cap_vecs * W;
     const unsigned long long V = V_left < max_vecs ? V_left : max_vecs;
     const size_t n = V == V_left ? left : static_cast<size_t>(V) * 8;
-    const unsigned long long per_cta_dim = oneshot ? V : (V + W - 1) / W;
-    const int grid = grid_for(c, per_cta_dim, U);
     cudaError_t e;
-    switch (mode) {
-      case B2_F32_WIRE_BF16:
-        e = launch_by_world<B2_F32_WIRE_BF16>(c, kind, grid, p, n, scale, s);
-        break;
-      case B2_F32:
-        e = launch_by_world<B2_F32>(c, kind, grid, p, n, scale, s);
-        break;
-      default:
-        e = launch_by_world<B2_BF16>(c, kind, grid, p, n, scale, s);
-        break;
+    if (!oneshot && V * wvb >= c->split_min_wire_bytes && V >= 2ull * W) {
+      // two concurrent half-collectives: lane 1 (second half) on the internal stream, lane 0 on the caller's
+      const unsigned long long V0 = (V / 2 + W - 1) / W * W;  // whole vecs, W-aligned so both halves slice evenly
+      const size_t n0 = static_cast<size_t>(V0) * 8;
+      B2_CUDA(cudaEventRecord(c->ev_fork, s));
+      B2_CUDA(cudaStreamWaitEvent(c->lane_stream, c->ev_fork, 0));
+      e = launch_mode(c->d1, mode, kind, grid_for(c, (V - V0 + W - 1) / W, U), p + n0 * elem_bytes(mode), n - n0, scale, c->lane_stream);
+      if (e == cudaSuccess) e = launch_mode(c->d, mode, kind, grid_for(c, V0 / W, U), p, n0, scale, s);
+      if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
+      B2_CUDA(cudaEventRecord(c->ev_join, c->lane_stream));
+      B2_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+      c->launches += 2;
+    } else {
+      const unsigned long long per_cta_dim = oneshot ? V : (V + W - 1) / W;
+      e = launch_mode(c->d, mode, kind, grid_for(c, per_cta_dim, U), p, n, scale, s);
+      if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
+      c->launches++;
     }
-    if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
-    c->launches++;
     p += n * elem_bytes(mode);
     left -= n;
   }
