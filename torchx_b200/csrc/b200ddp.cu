@@ -1025,7 +1025,9 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
     return fail(B2_EINVAL, "stage_bytes=%zu too small for world=%d", stage_bytes, world);
   layout(c, world, stage_bytes);
   c->d.timeout_ns = c->d1.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
-  c->split_min_wire_bytes = env_size("B2_SPLIT_MIN_BYTES", 4u << 20);
+  // Measured on 4xB200 (profiles/r01_lane_split_w4.md): two symmetric half-collectives hit their barriers at the same time,
+  // so the split buys nothing at 4-32 MiB and costs 6-19 % above 64 MiB.  Off by default; B2_SPLIT_MIN_BYTES enables it.
+  c->split_min_wire_bytes = env_size("B2_SPLIT_MIN_BYTES", ~static_cast<size_t>(0));
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
   c->auto_twoshot = env_size("B2_AUTO_TWOSHOT", B2_ALGO_TWOSHOT) == B2_ALGO_TWOSHOT_PULL ? B2_ALGO_TWOSHOT_PULL : B2_ALGO_TWOSHOT;
