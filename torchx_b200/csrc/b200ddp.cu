@@ -336,8 +336,10 @@ __device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
     st_release_sys(theirs, seq);
     unsigned long long t0 = 0;
     unsigned spins = 0;
-    // poll with a relaxed load (no fence per iteration); ONE acquire fence after the flag has been seen
-    while (static_cast<int32_t>(ld_relaxed_sys(mine) - seq) < 0) {
+    // Poll with ld.acquire.sys itself.  The alternative (relaxed polling + one fence.acq_rel.sys at the end) was measured
+    // on 4xB200 and DOUBLED the cost of the second barrier (5 -> 11 us): the standalone fence is a full MEMBAR.SYS that
+    // also drains this SM's outstanding stores, the acquire load is not.
+    while (static_cast<int32_t>(ld_acquire_sys(mine) - seq) < 0) {
       if ((++spins & 63u) == 0) {
         const unsigned long long now = globaltimer_ns();
         if (t0 == 0) {
@@ -349,7 +351,6 @@ __device__ __forceinline__ void cta_xbar(const CommDev& c, uint32_t seq) {
         }
       }
     }
-    fence_acq_rel_sys();
   }
   __syncthreads();  // peers' data is now visible to every thread of this CTA
 }
