@@ -1007,6 +1007,7 @@ void layout(b2_comm* c, int world, size_t stage_bytes) {
   cap &= ~static_cast<size_t>(255);
   c->stage_bytes = cap * (world + 1);
   const size_t stages0 = kLanes * kFlagRegionBytes;
+  const int lanes = c->split_min_wire_bytes == ~static_cast<size_t>(0) ? 1 : kLanes;  // lane 1 costs memory only when enabled
   for (int lane = 0; lane < kLanes; ++lane) {
     CommDev& d = lane == 0 ? c->d : c->d1;
     d.slice_cap = cap;
@@ -1014,7 +1015,7 @@ void layout(b2_comm* c, int world, size_t stage_bytes) {
     d.stage_off[0] = stages0 + (2 * lane + 0) * c->stage_bytes;
     d.stage_off[1] = stages0 + (2 * lane + 1) * c->stage_bytes;
   }
-  c->arena_bytes = stages0 + 2 * kLanes * c->stage_bytes;
+  c->arena_bytes = stages0 + 2 * lanes * c->stage_bytes;
 }
 
 int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
@@ -1024,11 +1025,11 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
   if (stage_bytes == 0) stage_bytes = env_size("B2_STAGE_MB", kDefaultStageBytes >> 20) << 20;
   if (stage_bytes < (static_cast<size_t>(world + 1) << 12))
     return fail(B2_EINVAL, "stage_bytes=%zu too small for world=%d", stage_bytes, world);
-  layout(c, world, stage_bytes);
   c->d.timeout_ns = c->d1.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
   // Measured on 4xB200 (profiles/r01_lane_split_w4.md): two symmetric half-collectives hit their barriers at the same time,
   // so the split buys nothing at 4-32 MiB and costs 6-19 % above 64 MiB.  Off by default; B2_SPLIT_MIN_BYTES enables it.
   c->split_min_wire_bytes = env_size("B2_SPLIT_MIN_BYTES", ~static_cast<size_t>(0));
+  layout(c, world, stage_bytes);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
   c->auto_twoshot = env_size("B2_AUTO_TWOSHOT", B2_ALGO_TWOSHOT) == B2_ALGO_TWOSHOT_PULL ? B2_ALGO_TWOSHOT_PULL : B2_ALGO_TWOSHOT;
