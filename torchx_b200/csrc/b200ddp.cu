@@ -933,7 +933,8 @@ constexpr uint64_t kShmMagic = 0x42323030444450ull;  // "B200DDP"
 
 struct ShmSlot {
   cudaIpcMemHandle_t handle;
-  int device;
+  int device;        // the rank's ordinal in ITS OWN numbering (CUDA_VISIBLE_DEVICES may differ between ranks)
+  char bus_id[24];   // PCI bus id: the identity that is comparable across processes
   int pid;
   unsigned long long arena_bytes;
   std::atomic<uint32_t> ready;  // 1 once handle/device/pid are valid
@@ -1293,6 +1294,8 @@ int b2_comm_create(b2_comm_t** out, int rank, int world, int device, const char*
     if (e != cudaSuccess) rc = fail(B2_ECUDA, "cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
     if (rc == B2_OK) {
       me.device = device;
+      memset(me.bus_id, 0, sizeof(me.bus_id));
+      cudaDeviceGetPCIBusId(me.bus_id, sizeof(me.bus_id), device);
       me.pid = static_cast<int>(getpid());
       me.arena_bytes = c->arena_bytes;
       if (rank == 0) {
@@ -1321,11 +1324,19 @@ int b2_comm_create(b2_comm_t** out, int rank, int world, int device, const char*
                   ps.arena_bytes, c->arena_bytes);
         break;
       }
-      if (ps.device != device) {
+      // Resolve the peer's GPU in THIS process's numbering by bus id.  If it is not visible here (each "node" of a
+      // multi-node-on-one-box job gets its own CUDA_VISIBLE_DEVICES) the P2P query is impossible, but CUDA >= 10.1 can
+      // still open an IPC mapping of an invisible peer's memory, so we just try.
+      int peer_local = -1;
+      if (cudaDeviceGetByPCIBusId(&peer_local, ps.bus_id) != cudaSuccess) {
+        cudaGetLastError();
+        peer_local = -1;
+      }
+      if (peer_local >= 0 && peer_local != device) {
         int can = 0;
-        cudaDeviceCanAccessPeer(&can, device, ps.device);
+        cudaDeviceCanAccessPeer(&can, device, peer_local);
         if (!can) {
-          rc = fail(B2_ENOPEER, "device %d cannot access rank %d's device %d over P2P", device, r, ps.device);
+          rc = fail(B2_ENOPEER, "device %d cannot access rank %d's device %s over P2P", device, r, ps.bus_id);
           break;
         }
       }
