@@ -73,6 +73,8 @@ struct CommDev {
   unsigned long long stage_off[2];  // byte offsets of the two staging buffers inside an arena
   unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
                                     //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced"
+  uint32_t* stagger_ctr;            // local: number of split collectives whose lane-0 half has finished its scatter
+  int stagger_role;                 // 0 = none, 1 = signal after my scatter (lane 0), 2 = wait before my scatter (lane 1)
   unsigned long long* trace;        // optional (b2_comm_trace): per-CTA globaltimer stamps of the LAST collective,
                                     // 8 slots per CTA: start, A done, bar1 done, B done, bar2 done, C done
 };
@@ -373,6 +375,27 @@ __device__ __forceinline__ void op_end(const CommDev& c, uint32_t seq0) {
   }
 }
 
+// Staggered lanes: the lane-1 half of a split collective starts its scatter only when the lane-0 half has issued its own,
+// so each half's barriers fall into the other half's NVLink phases instead of coinciding with them.
+__device__ __forceinline__ void stagger_signal(const CommDev& c) {
+  if (c.stagger_role == 1 && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(c.stagger_ctr, 1u);
+}
+__device__ __forceinline__ void stagger_wait(const CommDev& c, uint32_t seq0) {
+  if (c.stagger_role != 2) return;
+  if (threadIdx.x == 0) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (static_cast<int32_t>(ld_volatile_u32(c.stagger_ctr) - (seq0 + 1u)) < 0) {
+      if ((++spins & 63u) == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > c.timeout_ns) break;  // lane 0 never came: proceed, the peer barriers will report it
+      }
+    }
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ void trace_stamp(const CommDev& c, int slot) {
   if (c.trace != nullptr && threadIdx.x == 0) c.trace[blockIdx.x * 8 + slot] = globaltimer_ns();
 }
@@ -646,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long first = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
   const unsigned long long my_recv = stage + c.rank * c.slice_cap;
   const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;
+  stagger_wait(c, seq0);
   trace_stamp(c, 0);
 
   // ---- phase A -------------------------------------------------------------------------------
@@ -674,6 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   }
   trace_stamp(c, 1);
+  stagger_signal(c);
   cta_xbar(c, seq0 * 4u + 1u);
   trace_stamp(c, 2);
 
@@ -965,6 +990,7 @@ struct b2_comm {
   cudaStream_t lane_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   size_t split_min_wire_bytes = 0;  // two-shot messages of at least this many wire bytes are split over the lanes
+  bool stagger = true;              // B2_STAGGER=0: start both halves together (the symmetric split)
   int device = -1;
   bool local_world = false;    // created by b2_comm_create_local (no IPC, no shm)
   bool peer_is_ipc[B2_MAX_WORLD] = {};
@@ -1030,6 +1056,7 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
   // Measured on 4xB200 (profiles/r01_lane_split_w4.md): two symmetric half-collectives hit their barriers at the same time,
   // so the split buys nothing at 4-32 MiB and costs 6-19 % above 64 MiB.  Off by default; B2_SPLIT_MIN_BYTES enables it.
   c->split_min_wire_bytes = env_size("B2_SPLIT_MIN_BYTES", ~static_cast<size_t>(0));
+  c->stagger = env_size("B2_STAGGER", 1) != 0;
   layout(c, world, stage_bytes);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
@@ -1043,6 +1070,7 @@ int alloc_rank_resources(b2_comm* c, int rank, int world, int device, size_t sta
   c->d.done = c->counters + 32;  // a different 128 B line
   c->d1.opseq = c->counters + 16;
   c->d1.done = c->counters + 48;
+  c->d.stagger_ctr = c->d1.stagger_ctr = c->counters + 60;
   B2_CUDA(cudaStreamCreateWithFlags(&c->lane_stream, cudaStreamNonBlocking));
   B2_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   B2_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
@@ -1508,8 +1536,17 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
       const size_t n0 = static_cast<size_t>(V0) * 8;
       B2_CUDA(cudaEventRecord(c->ev_fork, s));
       B2_CUDA(cudaStreamWaitEvent(c->lane_stream, c->ev_fork, 0));
-      e = launch_mode(c->d1, mode, kind, grid_for(c, (V - V0 + W - 1) / W, U), p + n0 * elem_bytes(mode), n - n0, scale, c->lane_stream);
-      if (e == cudaSuccess) e = launch_mode(c->d, mode, kind, grid_for(c, V0 / W, U), p, n0, scale, s);
+      // both halves must be co-resident (1 CTA per SM, 148 SMs): at most 64 CTAs each; lane 0 first so it is resident
+      // before lane 1's CTAs start waiting for its scatter (push variant only: the stagger hooks live in k_twoshot)
+      const bool stagger = c->stagger && kind == B2_ALGO_TWOSHOT;
+      CommDev d0 = c->d, d1 = c->d1;
+      d0.stagger_role = stagger ? 1 : 0;
+      d1.stagger_role = stagger ? 2 : 0;
+      int g0 = grid_for(c, V0 / W, U), g1 = grid_for(c, (V - V0 + W - 1) / W, U);
+      if (g0 > 64) g0 = 64;
+      if (g1 > 64) g1 = 64;
+      e = launch_mode(d0, mode, kind, g0, p, n0, scale, s);
+      if (e == cudaSuccess) e = launch_mode(d1, mode, kind, g1, p + n0 * elem_bytes(mode), n - n0, scale, c->lane_stream);
       if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
       B2_CUDA(cudaEventRecord(c->ev_join, c->lane_stream));
       B2_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
