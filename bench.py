@@ -161,6 +161,9 @@ class Trainer:
 
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29533")
+            # keep stdout to the ONE JSON line: this image's NCCL otherwise prints "NCCL version ..." there
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+                os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", rank=rank, world_size=world, device_id=self.device)
             self.ddp = TorchDDP(model, device_ids=[local_rank])
             if args.wire == "bf16":
