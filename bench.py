@@ -396,13 +396,14 @@ def main():
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
-        "dtype": "bf16 autocast compute; fp32 master gradients; %s on the wire" % args.wire,
+        "dtype": "bf16",
         "data": "synthetic",
         "impl": args.impl,
         "config": {
             "workload": "ResNet-50 bf16 dist.ddp training step (BASELINE.json configs[1]), B=%d/GPU, 3x224x224, channels_last, SGD momentum" % args.batch,
             "global_batch": args.batch * world,
             "parallelism": f"dp{world}",
+            "precision": "bf16 autocast compute, fp32 master weights and gradient buckets, %s on the wire" % args.wire,
             "l2": "inputs larger than L2: 154 MB batch + 97.5 MiB of gradient buckets per step exceed the 126 MB L2",
             "gradient_buckets_mib": getattr(tr.ddp, "bucket_sizes_mib", lambda: None)(),
         },
