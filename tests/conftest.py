@@ -9,6 +9,11 @@ os.environ.setdefault("B2_LOCAL_TMA_MIN_MB", "0")
 # ... and the two-lane split of large two-shot collectives (off by default: measured no gain, see b200ddp.cu).
 os.environ.setdefault("B2_SPLIT_MIN_BYTES", str(4 << 20))
 
+# The local_cuda app registry defaults to ~/.torchx_b200: keep test runs out of the home directory.
+import tempfile  # noqa: E402
+
+os.environ.setdefault("TORCHX_HOME", tempfile.mkdtemp(prefix="torchx_b200_test_home_"))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

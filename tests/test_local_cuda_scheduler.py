@@ -180,3 +180,30 @@ def test_world_size_2_gloo_ddp_through_runner_and_cli_component(tmp_path):
         lines = list(runner.log_lines(handle, "toy_ddp", 0))
         assert sum("exact=True same_on_all_ranks=True" in ln for ln in lines) == 2
         assert handle.startswith("local_cuda://torchx/toy_ddp-")
+
+
+def test_status_list_and_logs_resolve_from_another_process(tmp_path, monkeypatch):
+    """The app registry: a second scheduler instance (another `torchx status` invocation) sees apps it did not launch."""
+    monkeypatch.setenv("TORCHX_HOME", str(tmp_path / "home"))
+    out = tmp_path / "out"
+    out.mkdir()
+    a = create_scheduler("sess")
+    try:
+        with mock.patch.object(a, "_cuda_device_count", return_value=0):
+            app_id = a.submit(ddp(str(out), script=WORKER, j="1x2"), {"log_dir": str(tmp_path / "logs")})
+        b = create_scheduler("sess")  # stands in for a different process
+        try:
+            assert b.describe(app_id).state in (AppState.RUNNING, AppState.SUCCEEDED)
+            assert _wait(a, app_id).state == AppState.SUCCEEDED
+            d = b.describe(app_id)
+            assert d.state == AppState.SUCCEEDED and d.ui_url.endswith(app_id)
+            assert sorted(b.log_iter(app_id, "env_worker", 0, streams=Stream.STDOUT)) == ["[0]:hello from rank 0 attempt 0\n", "[1]:hello from rank 1 attempt 0\n"]
+            assert [(r.app_id, r.state) for r in b.list()] == [(app_id, AppState.SUCCEEDED)]
+            assert b.describe("never-launched") is None
+            with pytest.raises(RuntimeError, match="another process"):
+                b._cancel_existing(app_id)
+        finally:
+            b.close()
+        assert create_scheduler("other_session").list() == []
+    finally:
+        a.close()

@@ -58,6 +58,18 @@ class CmdCancel(SubCommand):
             runner.cancel(args.app_handle)
 
 
+class CmdList(SubCommand):
+    def add_arguments(self, subparser: argparse.ArgumentParser) -> None:
+        subparser.add_argument("-s", "--scheduler", type=str, default="local_cuda", help="scheduler whose apps to list")
+
+    def run(self, args: argparse.Namespace) -> None:
+        with get_runner() as runner:
+            apps = runner.list(args.scheduler)
+            print(f"{'APP HANDLE':60s} APP STATUS")
+            for a in apps:
+                print(f"{a.app_handle:60s} {a.state}")
+
+
 class CmdRunopts(SubCommand):
     def add_arguments(self, subparser: argparse.ArgumentParser) -> None:
         subparser.add_argument("scheduler", type=str, nargs="?", help="scheduler to dump the runopts for, dumps for all schedulers if not specified")

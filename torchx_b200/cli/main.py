@@ -9,7 +9,7 @@ from typing import Dict, List, Optional
 
 import torchx_b200
 from torchx_b200.cli.cmd_base import SubCommand
-from torchx_b200.cli.cmd_misc import CmdBuiltins, CmdCancel, CmdConfigure, CmdDescribe, CmdRunopts, CmdStatus
+from torchx_b200.cli.cmd_misc import CmdBuiltins, CmdCancel, CmdConfigure, CmdDescribe, CmdList, CmdRunopts, CmdStatus
 from torchx_b200.cli.cmd_log import CmdLog
 from torchx_b200.cli.cmd_run import CmdRun
 
@@ -20,6 +20,7 @@ def get_sub_cmds() -> Dict[str, SubCommand]:
         "cancel": CmdCancel(),
         "configure": CmdConfigure(),
         "describe": CmdDescribe(),
+        "list": CmdList(),
         "log": CmdLog(),
         "run": CmdRun(),
         "runopts": CmdRunopts(),

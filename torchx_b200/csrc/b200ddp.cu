@@ -98,12 +98,6 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -1120,11 +1114,6 @@ int grid_for(const b2_comm* c, unsigned long long vecs_per_cta_dim, int unroll) 
   if (g < 1) g = 1;
   if (g > static_cast<unsigned long long>(cap)) g = cap;
   return static_cast<int>(g);
-}
-
-template <int W>
-constexpr int unroll_of() {
-  return dev::Unroll<W>::kU;
 }
 
 int unroll_for_world(int w) { return w >= 8 ? 1 : (w >= 4 ? 2 : (w >= 2 ? 4 : 8)); }

@@ -21,11 +21,16 @@ torchx/components/dist.py:261-308) and replaces what ``local_cwd`` + ``torchrun`
     the ``[rank]:``-prefixed merge of the workers' streams (what ``--tee 3`` prints), per-worker files live under
     ``attempt_<n>/rank_<local_rank>/``; ``error.json`` / ``SUCCESS`` as before, so ``torchx log|status`` work unchanged.
 
+  * app registry: every scheduled app leaves ``$TORCHX_HOME/apps/<session>/<app_id>.json`` (default ``~/.torchx_b200``) pointing
+    at its log tree, so ``torchx status | log | list`` also resolve from ANOTHER process (the reference's local scheduler
+    keeps state in the submitting process only and ``list()`` raises, local_scheduler.py:615,1099-1102).
+
 Roles whose command is not a torchrun line (e.g. ``utils.echo``) are launched exactly as ``local_cwd`` would.
 """
 from __future__ import annotations
 
 import io
+import json
 import logging
 import os
 import pprint
@@ -38,7 +43,7 @@ import time
 from dataclasses import asdict, dataclass, field
 from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
 
-from torchx_b200.schedulers.api import DescribeAppResponse
+from torchx_b200.schedulers.api import DescribeAppResponse, ListAppResponse, Stream, filter_regex, split_lines_iterator
 from torchx_b200.schedulers.local_scheduler import (
     COMBINED_LOG,
     ENV_CUDA_VISIBLE_DEVICES,
@@ -49,6 +54,7 @@ from torchx_b200.schedulers.local_scheduler import (
     ImageProvider,
     LocalOpts,
     LocalScheduler,
+    LogIterator,
     Opts,
     PopenRequest,
     ReplicaParam,
@@ -56,7 +62,7 @@ from torchx_b200.schedulers.local_scheduler import (
     _LocalReplica,
 )
 from torchx_b200.schedulers.ids import make_unique
-from torchx_b200.specs.api import AppDef, AppDryRunInfo, AppState, Role, is_terminal, runopts
+from torchx_b200.specs.api import NONE, AppDef, AppDryRunInfo, AppState, CfgVal, Role, is_terminal, runopts
 
 log = logging.getLogger(__name__)
 
@@ -314,6 +320,49 @@ def gpu_numa_cpus(device: int) -> List[int]:
         return []
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# cross-process app registry
+# ---------------------------------------------------------------------------------------------------------------
+def registry_dir(session_name: str) -> str:
+    home = os.environ.get("TORCHX_HOME") or os.path.join(os.path.expanduser("~"), ".torchx_b200")
+    return os.path.join(home, "apps", session_name or "default")
+
+
+def _pid_alive(pid: int) -> bool:
+    try:
+        os.kill(pid, 0)
+    except ProcessLookupError:
+        return False
+    except PermissionError:
+        return True
+    return True
+
+
+class _AppRecord:
+    """What another process can learn about an app: registry entry + the ``SUCCESS`` manifest in its log tree."""
+
+    def __init__(self, path: str) -> None:
+        with open(path) as f:
+            self.entry: Dict[str, Any] = json.load(f)
+        self.app_id: str = self.entry["app_id"]
+        self.log_dir: str = self.entry["log_dir"]
+
+    def manifest(self) -> Optional[Dict[str, Any]]:
+        try:
+            with open(os.path.join(self.log_dir, "SUCCESS")) as f:
+                return json.load(f)
+        except (OSError, ValueError):
+            return None
+
+    def state(self) -> Tuple[AppState, int]:
+        m = self.manifest()
+        if m is not None:
+            return AppState[m.get("final_state", "UNKNOWN")], int(m.get("num_restarts", 0))
+        if _pid_alive(int(self.entry.get("launcher_pid", -1))):
+            return AppState.RUNNING, 0
+        return AppState.UNKNOWN, 0  # launcher gone without closing the app (killed -9): nothing supervises it any more
+
+
 def _free_port() -> int:
     with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
         s.bind(("127.0.0.1", 0))
@@ -501,9 +550,46 @@ class LocalCudaScheduler(LocalScheduler):
             self._spawn_attempt(app, 0)
             app.set_state(AppState.RUNNING)
             self._apps[req.app_id] = app
+            self._register(app)
         app.monitor = threading.Thread(target=self._monitor, args=(app,), name=f"monitor-{req.app_id}", daemon=True)
         app.monitor.start()
         return req.app_id
+
+    # -- registry -----------------------------------------------------------------------------------------------------
+    def _register(self, app: "_CudaApp") -> None:
+        try:
+            d = registry_dir(self.session_name)
+            os.makedirs(d, exist_ok=True)
+            entry = {"app_id": app.id, "log_dir": app.log_dir, "launcher_pid": os.getpid(), "created": time.time(),
+                     "scheduler": self.backend, "roles": {r: len(g) for r, g in app.request.groups.items()}}
+            tmp = os.path.join(d, f".{app.id}.tmp")
+            with open(tmp, "w") as f:
+                json.dump(entry, f)
+            os.replace(tmp, os.path.join(d, f"{app.id}.json"))
+        except OSError as e:  # the registry is a convenience; never fail a launch over it
+            log.debug("could not write the app registry entry: %s", e)
+
+    def _record(self, app_id: str) -> Optional[_AppRecord]:
+        path = os.path.join(registry_dir(self.session_name), f"{app_id}.json")
+        try:
+            return _AppRecord(path)
+        except (OSError, ValueError, KeyError):
+            return None
+
+    def list(self, cfg: Optional[Mapping[str, CfgVal]] = None) -> List[ListAppResponse]:  # type: ignore[override]
+        """Apps of this session known to the registry (newest first), whichever process launched them."""
+        d = registry_dir(self.session_name)
+        out: List[Tuple[float, ListAppResponse]] = []
+        for name in (os.listdir(d) if os.path.isdir(d) else []):
+            if not name.endswith(".json"):
+                continue
+            rec = self._record(name[:-5])
+            if rec is None:
+                continue
+            live = self._apps.get(rec.app_id)
+            state = live.state if live is not None else rec.state()[0]
+            out.append((float(rec.entry.get("created", 0)), ListAppResponse(app_id=rec.app_id, state=state, name=rec.app_id.rsplit("-", 1)[0])))
+        return [r for _, r in sorted(out, key=lambda t: -t[0])]
 
     # -- supervision --------------------------------------------------------------------------------------------------
     def _monitor(self, app: _CudaApp) -> None:
@@ -537,7 +623,12 @@ class LocalCudaScheduler(LocalScheduler):
     def describe(self, app_id: str) -> Optional[DescribeAppResponse]:
         app = self._apps.get(app_id)
         if app is None:
-            return None
+            rec = self._record(app_id)  # launched by another process?
+            if rec is None or not os.path.isdir(rec.log_dir):
+                return None
+            state, restarts = rec.state()
+            return DescribeAppResponse(app_id=app_id, state=state, num_restarts=restarts, structured_error_msg=NONE,
+                                       ui_url=f"file://{rec.log_dir}", msg="state recovered from the app registry")
         with app.lock:
             err = app.get_structured_error_msg()
             if is_terminal(app.state):
@@ -546,8 +637,24 @@ class LocalCudaScheduler(LocalScheduler):
             return DescribeAppResponse(app_id=app_id, state=app.state, num_restarts=app.num_restarts, structured_error_msg=err,
                                        ui_url=f"file://{app.log_dir}", msg=msg or "<NONE>")
 
+    def log_iter(self, app_id: str, role_name: str, k: int = 0, regex: Optional[str] = None, since: Optional[Any] = None,
+                 until: Optional[Any] = None, should_tail: bool = False, streams: Optional[Stream] = None) -> Any:
+        if app_id in self._apps:
+            return super().log_iter(app_id, role_name, k, regex, since, until, should_tail, streams)
+        rec = self._record(app_id)
+        if rec is None:
+            raise KeyError(app_id)
+        name = {None: COMBINED_LOG, Stream.COMBINED: COMBINED_LOG, Stream.STDOUT: STDOUT_LOG, Stream.STDERR: STDERR_LOG}[streams]
+        log_file = os.path.join(rec.log_dir, role_name, str(k), name)
+        if not os.path.isfile(log_file):
+            raise RuntimeError(f"app: {app_id} has no log file {log_file}")
+        lines = split_lines_iterator(LogIterator(app_id, log_file, self, should_tail=should_tail))
+        return filter_regex(regex, lines) if regex else lines
+
     def _cancel_existing(self, app_id: str) -> None:
-        app = self._apps[app_id]
+        app = self._apps.get(app_id)
+        if app is None:
+            raise RuntimeError(f"app {app_id} was launched by another process; only its launcher can cancel it")
         if isinstance(app, _CudaApp):
             app.stop_monitor.set()
         with app.lock:
