@@ -207,3 +207,18 @@ def test_status_list_and_logs_resolve_from_another_process(tmp_path, monkeypatch
         assert create_scheduler("other_session").list() == []
     finally:
         a.close()
+
+
+def test_two_nodes_of_two_workers_on_one_box_gloo(tmp_path):
+    """The reference's own distributed integration case is `dist.ddp -j 2x2` on one host
+    (torchx/components/integration_tests/component_provider.py:39-51): two replicas ("nodes") x two workers, world 4."""
+    script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "toy_ddp.py")
+    with get_runner() as runner:
+        handle = runner.run_component("dist.ddp", ["-j", "2x2", "--script", script], "local_cuda", cfg={"log_dir": str(tmp_path / "logs"), "devices": []})
+        status = runner.wait(handle, wait_interval=0.2)
+        assert status is not None and status.state == AppState.SUCCEEDED, status
+        per_node = [list(runner.log_lines(handle, "toy_ddp", k)) for k in (0, 1)]
+        ranks = sorted(int(m) for lines in per_node for ln in lines for m in __import__("re").findall(r"rank (\d)/4", ln))
+        assert ranks == [0, 1, 2, 3]
+        assert all("same_on_all_ranks=True" in ln for lines in per_node for ln in lines if "sha256" in ln)
+        assert any(ln.startswith("[2]:") or ln.startswith("[3]:") for ln in per_node[1])  # node 1 hosts global ranks 2, 3
