@@ -46,7 +46,22 @@ def local_cuda_device() -> torch.device:
 
 
 def local_device() -> torch.device:
-    return local_cuda_device() if torch.cuda.is_available() else torch.device("cpu")
+    """The device this process should place its model on: ``cuda:<pinned ordinal>`` when the B200 communicator or an
+    nccl process group is active, ``cpu`` under any other process group; with nothing initialised, ``cuda`` if the host
+    has GPUs else ``cpu`` (reference torchx/distributed/__init__.py:70-88)."""
+    if _COMM is not None:
+        return torch.device("cuda", _COMM.device)
+    if dist.is_available() and dist.is_initialized():
+        return local_cuda_device() if dist.get_backend() == "nccl" else torch.device("cpu")
+    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+
+
+def is_rank0() -> bool:
+    return rank() == 0
+
+
+def is_local_rank0() -> bool:
+    return local_rank() == 0
 
 
 def communicator() -> Any:
@@ -85,7 +100,7 @@ def init_pg(backend: str = "auto", **kwargs: Any) -> torch.device:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "0")
         dist.init_process_group(backend=backend, rank=0, world_size=1, **kwargs)
-    dev = local_device() if backend == "nccl" else torch.device("cpu")
+    dev = local_cuda_device() if backend == "nccl" else torch.device("cpu")
     if dev.type == "cuda":
         torch.cuda.set_device(dev)
     return dev
