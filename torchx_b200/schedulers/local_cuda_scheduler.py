@@ -363,6 +363,18 @@ class _AppRecord:
         return AppState.UNKNOWN, 0  # launcher gone without closing the app (killed -9): nothing supervises it any more
 
 
+def _unlink_rendezvous_blocks(shm_name: str) -> None:
+    """Rank 0 unlinks the control block once everyone has mapped it; a gang that died mid-rendezvous leaves it behind.
+    POSIX shm objects live under /dev/shm on Linux: remove whatever this app's epochs left there."""
+    import glob
+
+    for path in glob.glob(f"/dev/shm/{shm_name.lstrip('/')}_*"):
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+
+
 def _free_port() -> int:
     with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
         s.bind(("127.0.0.1", 0))
@@ -547,6 +559,7 @@ class LocalCudaScheduler(LocalScheduler):
                     mux.role = role_name  # type: ignore[attr-defined]
                     app.muxes.append(mux)
             app.extra_closers.append(lambda: [m.close() for m in app.muxes])
+            app.extra_closers.append(lambda: _unlink_rendezvous_blocks(req.shm_name))
             self._spawn_attempt(app, 0)
             app.set_state(AppState.RUNNING)
             self._apps[req.app_id] = app
