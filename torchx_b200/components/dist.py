@@ -97,29 +97,26 @@ def ddp(
     Note: (cpu, gpu, memMB) are mutually exclusive with ``h`` (named resource); ``h`` wins when given.
 
     Args:
-        script_args: arguments to the main module
-        script: script or binary to run within the image
-        m: the python module path to run
-        image: image (e.g. docker); ignored by the local schedulers, where the cwd is the image
-        name: job name override in the following format: ``{experimentname}/{runname}`` or ``{experimentname}/`` or ``/{runname}`` or ``{runname}``.
-            Uses the script or module name if ``{runname}`` not specified.
-        cpu: number of cpus per replica
-        gpu: number of gpus per replica
-        memMB: cpu memory in MB per replica
-        h: a registered named resource (if specified takes precedence over cpu, gpu, memMB)
-        j: [{min_nnodes}:]{nnodes}x{nproc_per_node}, for gpu hosts, nproc_per_node must not exceed num gpus
-        env: environment varibles to be passed to the run (e.g. ENV1=v1,ENV2=v2,ENV3=v3)
-        metadata: metadata to be passed to the scheduler (e.g. KEY1=v1,KEY2=v2,KEY3=v3)
-        max_retries: the number of scheduler retries allowed
-        rdzv_port: the port on rank0's host to use for hosting the c10d store used for rendezvous.
-                   Only takes effect when running multi-node. When running single node, this parameter
-                   is ignored and a random free port is chosen.
-        rdzv_backend: the rendezvous backend to use. Only takes effect when running multi-node.
-        rdzv_conf: the additional rendezvous configuration to use (ex. join_timeout=600,close_timeout=600,timeout=600).
-        mounts: mounts to mount into the worker environment/container (ex. type=<bind/volume>,src=/host,dst=/job[,readonly]).
-                Not supported by the local schedulers.
-        debug: whether to run with preset debug flags enabled
-        tee: tees the specified std stream(s) to console + file. 0: none, 1: stdout, 2: stderr, 3: both
+        script_args: argv of the training program
+        script: training script to launch on every worker
+        m: training module to launch with ``python -m`` instead of a script
+        image: recorded in the AppDef (container schedulers); the local schedulers run from the cwd
+        name: ``{experiment}/{run}``, ``{experiment}/``, ``/{run}`` or ``{run}``; the run name defaults to the script or
+            module name
+        cpu: cores requested per replica
+        gpu: GPUs requested per replica
+        memMB: host memory requested per replica, MB
+        h: named resource; wins over cpu / gpu / memMB when given
+        j: [{min_nnodes}:]{nnodes}x{nproc_per_node}; on GPU hosts nproc_per_node must not exceed the GPU count
+        env: extra environment for the workers, e.g. A=1,B=2
+        metadata: scheduler metadata, e.g. K1=v1,K2=v2
+        max_retries: scheduler-level retries (gang re-launch on local_cuda)
+        rdzv_port: c10d store port on rank 0's host; multi-node only (a single node uses a random free port)
+        rdzv_backend: torchrun rendezvous backend; multi-node only
+        rdzv_conf: extra rendezvous settings, e.g. join_timeout=600,timeout=600
+        mounts: container mounts; rejected here (no containers on the single-box path)
+        debug: apply the debug environment preset
+        tee: which worker streams torchrun also copies to the console: 0 none, 1 stdout, 2 stderr, 3 both
     """
     if (script is None) == (m is None):
         raise ValueError("exactly one of --script and -m must be specified")
@@ -186,18 +183,18 @@ def spmd(
     from the GPU count of the named resource ``h``.
 
     Args:
-        args: the arguments to the main module or script (e.g. my/trainer.py -foo bar)
-        script: path of the main script
-        m: the main module name (e.g. my.module.trainer), run as ``python -m``
-        image: the base image of the job (ignored by the local schedulers)
-        name: ``{experimentname}/{runname}`` or ``{experimentname}/`` or ``/{runname}`` or ``{runname}``
-        h: the type of host to run on. Must be one of the registered named resources
-        j: {nnodes}x{nproc_per_node}. For GPU hosts omitting nproc_per_node will infer it from the GPU count on the host
-        env: environment variables to be passed to the run (e.g. ENV1=v1,ENV2=v2,ENV3=v3)
-        metadata: metadata to be passed to the scheduler (e.g. KEY1=v1,KEY2=v2,KEY3=v3)
-        max_retries: the number of scheduler retries allowed
-        mounts: not supported on the single-box path
-        debug: whether to run with preset debug flags enabled
+        args: argv of the program
+        script: program file
+        m: program module (``python -m``)
+        image: recorded in the AppDef; the local schedulers run from the cwd
+        name: ``{experiment}/{run}`` (either side optional)
+        h: named resource describing one host
+        j: {nnodes}x{nproc_per_node}; without the ``x`` part nproc_per_node is the host's GPU count
+        env: extra environment, e.g. A=1,B=2
+        metadata: scheduler metadata, e.g. K1=v1,K2=v2
+        max_retries: scheduler-level retries
+        mounts: rejected (no containers on the single-box path)
+        debug: apply the debug environment preset
     """
     return ddp(*args, script=script, m=m, image=image, name=name, h=h, j=str(StructuredJArgument.parse_from(h, j)),
                env=env or {}, metadata=metadata, max_retries=max_retries, mounts=mounts, debug=debug)

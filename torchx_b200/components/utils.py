@@ -11,12 +11,12 @@ from torchx_b200 import specs
 
 def echo(msg: str = "hello world", image: str = torchx_b200.IMAGE, num_replicas: int = 1) -> specs.AppDef:
     """
-    Echos a message to stdout (calls echo)
+    Prints ``msg`` on every replica (the ``echo`` binary) - the smallest possible scheduler smoke test.
 
     Args:
-        msg: message to echo
-        image: image to use
-        num_replicas: number of replicas to run
+        msg: text to print
+        image: recorded in the AppDef; the local schedulers run from the cwd
+        num_replicas: how many copies to start
     """
     return specs.AppDef(name="echo", roles=[specs.Role(name="echo", image=image, entrypoint="echo", args=[msg],
                                                       num_replicas=num_replicas, resource=specs.resource(cpu=1, gpu=0, memMB=1024))])
@@ -24,11 +24,11 @@ def echo(msg: str = "hello world", image: str = torchx_b200.IMAGE, num_replicas:
 
 def touch(file: str, image: str = torchx_b200.IMAGE) -> specs.AppDef:
     """
-    Touches a file (calls touch)
+    Creates an empty file (the ``touch`` binary); tests use it to observe macro substitution in arguments.
 
     Args:
-        file: file to create
-        image: the image to use
+        file: path of the file
+        image: recorded in the AppDef; the local schedulers run from the cwd
     """
     return specs.AppDef(name="touch", roles=[specs.Role(name="touch", image=image, entrypoint="touch", args=[file],
                                                        num_replicas=1, resource=specs.resource(cpu=1, gpu=0, memMB=1024))])
@@ -37,19 +37,18 @@ def touch(file: str, image: str = torchx_b200.IMAGE) -> specs.AppDef:
 def sh(*args: str, image: str = torchx_b200.IMAGE, num_replicas: int = 1, cpu: int = 1, gpu: int = 0, memMB: int = 1024,
        h: Optional[str] = None, env: Optional[Dict[str, str]] = None, max_retries: int = 0) -> specs.AppDef:
     """
-    Runs the provided command via sh. Currently sh does not support
-    environment variable substitution.
+    Joins ``args`` into one ``sh -c`` command line.  ``$`` is escaped, so no variable expansion happens in the shell.
 
     Args:
-        args: bash arguments
-        image: image to use
-        num_replicas: number of replicas to run
-        cpu: number of cpus per replica
-        gpu: number of gpus per replica
-        memMB: cpu memory in MB per replica
-        h: a registered named resource (if specified takes precedence over cpu, gpu, memMB)
-        env: environment varibles to be passed to the run (e.g. ENV1=v1,ENV2=v2,ENV3=v3)
-        max_retries: the number of scheduler retries allowed
+        args: words of the command
+        image: recorded in the AppDef; the local schedulers run from the cwd
+        num_replicas: how many copies to start
+        cpu: cores requested per replica
+        gpu: GPUs requested per replica
+        memMB: host memory requested per replica, MB
+        h: named resource; wins over cpu / gpu / memMB when given
+        env: extra environment, e.g. A=1,B=2
+        max_retries: scheduler-level retries (gang re-launch on local_cuda)
     """
     escaped = " ".join(shlex.quote(a).replace("$", "\\$") for a in args)
     return specs.AppDef(name="sh", roles=[specs.Role(name="sh", image=image, entrypoint="sh", args=["-c", escaped],
@@ -61,22 +60,21 @@ def python(*args: str, m: Optional[str] = None, c: Optional[str] = None, script:
            name: str = "torchx_utils_python", cpu: int = 1, gpu: int = 0, memMB: int = 1024, h: Optional[str] = None,
            num_replicas: int = 1) -> specs.AppDef:
     """
-    Runs ``python`` with the specified module, command or script on the specified
-    image and host. Use ``--`` to separate component args and program args
-    (e.g. ``torchx run utils.python --m foo.main -- --args to --main``)
+    Starts the interpreter on exactly one of: a module (``-m``), an inline program (``-c``) or a script file.  Program
+    arguments follow a ``--`` separator: ``torchx run utils.python -m pkg.main -- --flag value``.
 
     Args:
-        args: arguments passed to the program in sys.argv[1:] (ignored with `--c`)
-        m: run library module as a script
-        c: program passed as string (may error if scheduler has a length limit on args)
-        script: .py script to run
-        image: image to run on
-        name: name of the job
-        cpu: number of cpus per replica
-        gpu: number of gpus per replica
-        memMB: cpu memory in MB per replica
-        h: a registered named resource (if specified takes precedence over cpu, gpu, memMB)
-        num_replicas: number of copies to run (each on its own container)
+        args: the program's own argv (unused with ``-c``)
+        m: module to run as ``python -m``
+        c: source text to run as ``python -c``
+        script: path of a .py file
+        image: recorded in the AppDef; the local schedulers run from the cwd
+        name: job name
+        cpu: cores requested per replica
+        gpu: GPUs requested per replica
+        memMB: host memory requested per replica, MB
+        h: named resource; wins over cpu / gpu / memMB when given
+        num_replicas: how many copies to start
     """
     if sum(x is not None for x in (m, c, script)) != 1:
         raise ValueError("exactly one of `-m`, `-c` and `--script` needs to be specified")
