@@ -179,8 +179,13 @@ def test_comm_hook_on_stock_ddp_world1():
 
     from torchx_b200.ddp import B200HookState, Communicator, b200_bf16_compress_hook
 
-    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    os.environ.setdefault("MASTER_PORT", "29577")
+    import socket
+
+    with socket.socket() as sock:  # any free port: a fixed one could collide with another job on the box
+        sock.bind(("127.0.0.1", 0))
+        port = sock.getsockname()[1]
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=0, world_size=1)
     comm = Communicator.create(0, 1, 0, "/unused")
     try:
