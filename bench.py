@@ -160,7 +160,12 @@ class Trainer:
             from torch.nn.parallel import DistributedDataParallel as TorchDDP
 
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            os.environ.setdefault("MASTER_PORT", "29533")
+            if "MASTER_PORT" not in os.environ:  # plain `python bench.py --impl reference` (N=1): any free port
+                import socket
+
+                with socket.socket() as sock:
+                    sock.bind(("127.0.0.1", 0))
+                    os.environ["MASTER_PORT"] = str(sock.getsockname()[1])
             # keep stdout to the ONE JSON line: this image's NCCL otherwise prints "NCCL version ..." there
             if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
                 os.environ["NCCL_DEBUG"] = "WARN"
