@@ -480,7 +480,9 @@ class LocalScheduler(Scheduler[LocalOpts]):
         return subprocess.Popen(args=args, env=env, stdout=stdout, stderr=stderr, start_new_session=True, cwd=cwd,
                                 preexec_fn=preexec_fn)
 
-    def _popen(self, role_name: str, replica_id: int, p: ReplicaParam, preexec_fn: Optional[Callable[[], None]] = None) -> _LocalReplica:
+    def _popen(self, role_name: str, replica_id: int, replica_params: ReplicaParam,
+               preexec_fn: Optional[Callable[[], None]] = None) -> _LocalReplica:
+        p = replica_params
         out, err, comb = self._get_replica_output_handles(p)
         env = self._get_replica_env(p)
         log.debug("Running %s (replica %s):\n %s", role_name, replica_id, pprint.pformat(asdict(p), indent=2, width=80))

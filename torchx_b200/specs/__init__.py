@@ -67,16 +67,25 @@ class _NamedResources:
     def keys(self):
         return _all_named_resources().keys()
 
+    def __iter__(self):
+        return iter(_all_named_resources())
+
+    def __len__(self) -> int:
+        return len(_all_named_resources())
+
+    def items(self):
+        return ((k, f()) for k, f in _all_named_resources().items())
+
 
 named_resources = _NamedResources()
 
 
 def resource(cpu: Optional[int] = None, gpu: Optional[int] = None, memMB: Optional[int] = None, h: Optional[str] = None) -> Resource:
-    """``h`` (a named resource) wins over the raw values; unset raw values default to cpu=1, gpu=0, memMB=1024
-    (reference torchx/specs/__init__.py:148-181)."""
+    """``h`` (a named resource) wins over the raw values; unset (or zero) raw values default to cpu=2, gpu=0,
+    memMB=1024 (reference torchx/specs/__init__.py:148-181)."""
     if h:
         return named_resources[h]
-    return Resource(cpu=cpu if cpu is not None else 1, gpu=gpu if gpu is not None else 0, memMB=memMB if memMB is not None else 1024)
+    return Resource(cpu=cpu or 2, gpu=gpu or 0, memMB=memMB or 1024)
 
 
 def get_named_resources(res: str) -> Resource:

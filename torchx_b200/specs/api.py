@@ -318,9 +318,10 @@ class AppDryRunInfo(Generic[T]):
 # run options (scheduler cfg schema)
 # ---------------------------------------------------------------------------------------------------------------
 def get_type_name(tp: Any) -> str:
-    if getattr(tp, "__module__", "") != "typing" and hasattr(tp, "__name__") and not getattr(tp, "__args__", None):
+    """``int`` -> "int", ``list[str]`` -> "list", ``typing.List[str]`` -> "typing.List[str]" (reference api.py:822-829)."""
+    if getattr(tp, "__module__", "typing") != "typing" and hasattr(tp, "__name__"):
         return tp.__name__
-    return str(tp).replace("typing.", "")
+    return str(tp)
 
 
 class cases:
@@ -395,13 +396,17 @@ class runopts:
 
     @staticmethod
     def is_type(obj: CfgVal, tp: Any) -> bool:
-        if _is_list_of_str(tp):
-            return isinstance(obj, list) and all(isinstance(e, str) for e in obj)
-        if _is_dict_of_str(tp):
-            return isinstance(obj, dict) and all(isinstance(k, str) and isinstance(v, str) for k, v in obj.items())
+        """``isinstance`` that tolerates generic aliases: for ``List[str]`` / ``Dict[str, str]`` style types (where
+        ``isinstance`` raises) a list passes when all its elements are str and a dict when all keys and values are -
+        the reference is equally lenient about WHICH generic it was (api.py:912-927), and callers rely on that for
+        empty defaults."""
         try:
             return isinstance(obj, tp)
         except TypeError:
+            if isinstance(obj, list):
+                return all(isinstance(e, str) for e in obj)
+            if isinstance(obj, dict):
+                return all(isinstance(k, str) and isinstance(v, str) for k, v in obj.items())
             return False
 
     def add(self, cfg_key: str, type_: Any, help: str, default: CfgVal = None, required: bool = False) -> None:
