@@ -53,6 +53,16 @@ def to_dict(arg: str) -> Dict[str, str]:
     if not arg or not arg.strip():
         return {}
     eqs, delims = _scan(arg)
+    # Runs of '=' act as one separator and '=' signs with nothing after them are ignored, so a value cannot END in '='
+    # ("BAR=v3==" parses as BAR=v3) - a documented limitation of the reference's grammar (types_test.py:168-179).
+    merged: List[int] = []
+    for e in eqs:
+        if not arg[e + 1:].strip(" ="):
+            continue
+        if merged and not arg[merged[-1] + 1:e].strip(" ="):
+            continue
+        merged.append(e)
+    eqs = merged
     if not eqs:
         raise ValueError(f"`{arg}` does not have at least one `key=value` pair")
     key_starts = [0]
@@ -65,7 +75,7 @@ def to_dict(arg: str) -> Dict[str, str]:
     for i, eq in enumerate(eqs):
         key = arg[key_starts[i]:eq].strip()
         stop = key_starts[i + 1] - 1 if i + 1 < len(eqs) else len(arg)
-        raw = arg[eq + 1:stop].strip()
+        raw = arg[eq + 1:stop].strip().lstrip("=").strip() if i + 1 < len(eqs) else arg[eq + 1:stop].strip().strip("=").strip()
         if not key or not raw:
             raise ValueError(f"malformed key-value pair near `{arg[key_starts[i]:stop]}` in `{arg}`")
         out[key] = _unquote(raw)
@@ -77,11 +87,15 @@ def to_list(arg: str) -> List[str]:
 
 
 def _strip_optional(tp: Any) -> Tuple[Any, bool]:
-    origin = get_origin(tp)
-    if origin is Union or (hasattr(typing, "UnionType") and origin is getattr(__import__("types"), "UnionType", None)):
-        inner = [a for a in get_args(tp) if a is not type(None)]
-        if len(inner) == 1 and len(get_args(tp)) == 2:
-            return inner[0], True
+    """``Optional[X]`` / ``Union[X, None]`` / ``X | None`` -> (X, True); anything else -> (tp, False)."""
+    import types as _types
+
+    if get_origin(tp) is typing.Annotated:
+        tp = get_args(tp)[0]
+    if get_origin(tp) is Union or isinstance(tp, _types.UnionType):
+        args = get_args(tp)
+        if len(args) == 2 and args[1] is type(None):
+            return args[0], True
     return tp, False
 
 
@@ -111,6 +125,8 @@ def decode(value: Any, annotation: Any) -> Any:
         return tp(value)
     if origin in (list, List):
         (elem,) = get_args(tp) or (str,)
+        if not is_primitive(elem):
+            raise ValueError("List types support only primitives: int, str, float")
         return [decode(v, elem) for v in to_list(value)]
     if origin in (dict, Dict):
         kt, vt = get_args(tp) or (str, str)
@@ -124,12 +140,30 @@ def decode_optional(annotation: Any) -> Any:
     return _strip_optional(annotation)[0]
 
 
-def none_throws(x: Optional[Any], msg: str = "unexpected None") -> Any:
+def none_throws(x: Optional[Any], msg: str = "Unexpected `None`") -> Any:
     if x is None:
         raise AssertionError(msg)
     return x
 
 
 def get_argparse_param_type(tp: Any) -> Callable[[str], Any]:
-    base = _strip_optional(tp)[0]
-    return base if base in (int, float) else str
+    """argparse ``type=`` for a parameter: the primitive itself for int / float / str, ``str`` for everything that is
+    decoded later (lists, dicts, bools, Optionals).  Accepts an annotation or an ``inspect.Parameter``."""
+    if isinstance(tp, inspect.Parameter):
+        tp = tp.annotation
+    if get_origin(tp) is typing.Annotated:
+        tp = get_args(tp)[0]
+    return tp if tp in (int, float, str) else str
+
+
+def decode_from_string(encoded_value: str, annotation: Any) -> Any:
+    """``"a,b"`` -> list / ``"k=v,k2=v2"`` -> dict according to ``annotation``; empty input gives None; anything that is
+    not a list or dict type raises ``ValueError`` (reference torchx/util/types.py:174-207)."""
+    if not encoded_value:
+        return None
+    tp = annotation
+    if get_origin(tp) is typing.Annotated:
+        tp = get_args(tp)[0]
+    if get_origin(tp) in (list, List, dict, Dict):
+        return decode(encoded_value, tp)
+    raise ValueError(f"cannot decode {encoded_value!r} as {annotation!r}: only list and dict types are string-encoded")
