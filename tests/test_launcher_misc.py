@@ -209,23 +209,43 @@ def test_cli_dryrun_runopts_builtins_and_run(tmp_path, capsys):
 
 # ---- .torchxconfig ---------------------------------------------------------------------------------------------
 def test_torchxconfig_sections_and_precedence(tmp_path, monkeypatch):
+    """CLI > $TORCHXCONFIG (exclusive) > $HOME/.torchxconfig > ./.torchxconfig > runopt defaults (reference config.py:63-73)."""
+    monkeypatch.delenv("TORCHXCONFIG", raising=False)
     home, cwd = tmp_path / "home", tmp_path / "cwd"
     home.mkdir(); cwd.mkdir()
-    (home / ".torchxconfig").write_text("[local_cuda]\nlog_dir = /home/logs\npin_cpus = False\n[component:dist.ddp]\nj = 1x8\n")
-    (cwd / ".torchxconfig").write_text("[local_cuda]\nlog_dir = /cwd/logs\nstage_mb = None\n[cli:run]\nscheduler = local_cwd\n")
+    (home / ".torchxconfig").write_text("[local_cuda]\nlog_dir = /home/logs\npin_cpus = no\n[component:dist.ddp]\nj = 1x8\n")
+    (cwd / ".torchxconfig").write_text("[local_cuda]\nlog_dir = /cwd/logs\nstage_mb = None\ndevices = 2;3\nbogus = 1\n[cli:run]\nscheduler = local_cwd\n"
+                                       "[component:dist.ddp]\nj = 1x2\ncpu = 4\n")
     dirs = [str(home), str(cwd)]
-    assert config.get_config(None, "local_cuda", "log_dir", dirs) == "/cwd/logs"  # cwd wins over home
+    assert config.find_configs(dirs) == [str(home / ".torchxconfig"), str(cwd / ".torchxconfig")]
     assert config.get_config("cli", "run", "scheduler", dirs) == "local_cwd" and config.get_config("cli", "run", "nope", dirs) is None
-    assert config.load_sections("component", dirs) == {"dist.ddp": {"j": "1x8"}}
-    from torchx_b200.schedulers.local_cuda_scheduler import CudaOpts
-
+    assert config.load_sections("component", dirs) == {"dist.ddp": {"j": "1x8", "cpu": "4"}}  # user level wins per key
+    assert config.get_configs("component", "nope", dirs) == {}
     cfg = {"log_dir": "/explicit"}
-    config.apply("local_cuda", cfg, dirs, CudaOpts.as_runopts())
-    assert cfg == {"log_dir": "/explicit", "pin_cpus": False}  # CLI value wins; literal cast by the runopts; None skipped
+    config.apply("local_cuda", cfg, dirs)
+    assert cfg == {"log_dir": "/explicit", "pin_cpus": False, "stage_mb": None, "devices": ["2", "3"]}  # typed by the runopts; unknown key skipped
+    cfg2 = {}
+    config.apply("local_cuda", cfg2, dirs)
+    assert cfg2["log_dir"] == "/home/logs"
     explicit = tmp_path / "x.cfg"
     explicit.write_text("[local_cwd]\nprepend_cwd = True\n")
     monkeypatch.setenv("TORCHXCONFIG", str(explicit))
-    assert config.get_config(None, "local_cwd", "prepend_cwd") == "True" and config.get_config(None, "local_cuda", "log_dir") is None
+    assert config.find_configs(dirs) == [str(explicit)]
+    cfg3 = {}
+    config.apply("local_cwd", cfg3, dirs)
+    assert cfg3 == {"prepend_cwd": True}
+    monkeypatch.setenv("TORCHXCONFIG", "")
+    assert config.find_configs(dirs) == []
+    monkeypatch.setenv("TORCHXCONFIG", str(tmp_path / "missing"))
+    with pytest.raises(FileNotFoundError):
+        config.find_configs()
+    monkeypatch.delenv("TORCHXCONFIG")
+    out = io.StringIO()
+    config.dump(out, ["local_cuda"])
+    text = out.getvalue()
+    assert "[local_cuda]" in text and "pin_cpus = True" in text and "devices = None" in text
+    with pytest.raises(ValueError):
+        config.dump(io.StringIO(), ["nope"])
 
 
 # ---- plugins / registry ----------------------------------------------------------------------------------------

@@ -77,7 +77,7 @@ class CmdRun(SubCommand):
     def _run(self, runner: Runner, args: argparse.Namespace) -> None:
         opts = runner.scheduler_run_opts(args.scheduler)
         cfg = opts.cfg_from_str(args.scheduler_args or "")
-        config.apply(scheduler=args.scheduler, cfg=cfg, opts=opts)
+        config.apply(scheduler=args.scheduler, cfg=cfg)
         assert self._subparser is not None
         component, component_args = _parse_component_name_and_args(args.component_name_and_args, self._subparser)
         try:

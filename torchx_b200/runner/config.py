@@ -1,101 +1,179 @@
-"""``.torchxconfig``: INI defaults for scheduler cfg, the ``run`` sub-command and component arguments.
+"""``.torchxconfig``: INI defaults for scheduler cfg, CLI sub-commands and component arguments.
 
-Same file format, sections and lookup order as reference torchx/runner/config.py (apply:295, load_sections:336,
-get_config:446): ``$TORCHXCONFIG`` if set, else ``$HOME/.torchxconfig`` overlaid by ``./.torchxconfig`` (cwd wins);
-values given on the command line always win over the file.
+Same file format, section names and precedence as reference torchx/runner/config.py (dump:220, apply:295,
+load_sections:336, get_configs:421, get_config:446, find_configs:473, load:509).  Precedence, high to low:
 
-    [local_cuda]
-    log_dir = /tmp/torchx_logs
-    pin_cpus = True
+  1. values given on the command line / in code (``cfg`` entries are never overwritten);
+  2. the file named by ``$TORCHXCONFIG`` - if set it is the ONLY file read (empty value: no file at all);
+  3. otherwise ``$HOME/.torchxconfig`` (user level) overlaid on ``./.torchxconfig`` (project level): files are read in
+     that order and the FIRST file to define a key wins;
+  4. the defaults declared by the scheduler's runopts.
 
-    [cli:run]
+    [local_cuda]                     scheduler section: keys are the scheduler's runopts
+    log_dir = /tmp/torchx_logs       str / int / float literals
+    pin_cpus = True                  bool (configparser spellings: true/false/yes/no/on/off/1/0)
+    devices = 0;1;2;3                list of str, ';'-separated
+    stage_mb = None                  explicit None
+
+    [cli:run]                        defaults of a CLI sub-command's options (+ ``component`` for run)
     scheduler = local_cuda
     component = dist.ddp
 
-    [component:dist.ddp]
+    [component:dist.ddp]             defaults of a component's parameters (strings, decoded like CLI arguments)
     j = 1x8
 """
 from __future__ import annotations
 
 import configparser
+import logging
 import os
 from pathlib import Path
-from typing import Dict, List, Optional
+from typing import Dict, Iterable, List, Optional, TextIO
 
-from torchx_b200.settings import ENV_TORCHXCONFIG
-from torchx_b200.specs.api import CfgVal, runopts
+from torchx_b200 import settings
+from torchx_b200.schedulers import get_scheduler_factories
+from torchx_b200.schedulers.api import Scheduler
+from torchx_b200.specs.api import CfgVal, get_type_name, runopt
 
 CONFIG_FILE = ".torchxconfig"
+CONFIG_PREFIX_DELIM = ":"
+ENV_TORCHXCONFIG: str = settings.ENV_TORCHXCONFIG
 _NONE = "None"
 
-
-def find_configs(dirs: Optional[List[str]] = None) -> List[str]:
-    """Config files to read, lowest priority first."""
-    explicit = os.environ.get(ENV_TORCHXCONFIG)
-    if explicit:
-        if not Path(explicit).is_file():
-            raise FileNotFoundError(f"`{ENV_TORCHXCONFIG}={explicit}` does not exist or is not a file")
-        return [explicit]
-    roots = dirs if dirs is not None else [str(Path.home()), str(Path.cwd())]
-    return [str(Path(d) / CONFIG_FILE) for d in roots if (Path(d) / CONFIG_FILE).is_file()]
+log = logging.getLogger(__name__)
 
 
-def _parser(dirs: Optional[List[str]] = None) -> configparser.ConfigParser:
+DEFAULT_CONFIG_DIRS = [str(Path.home()), str(Path.cwd())]  # user level first: its keys win over the project's
+
+
+def _new_parser() -> configparser.ConfigParser:
     cp = configparser.ConfigParser()
-    cp.optionxform = str  # type: ignore[assignment]  # keys are case sensitive
-    for path in find_configs(dirs):
-        cp.read(path)
+    cp.optionxform = lambda option: option  # type: ignore[assignment]  # option names are case sensitive
     return cp
 
 
-def get_config(prefix: Optional[str], name: str, key: str, dirs: Optional[List[str]] = None) -> Optional[str]:
-    """Value of ``key`` in section ``[prefix:name]`` (or ``[name]`` when prefix is empty), else None."""
-    section = f"{prefix}:{name}" if prefix else name
-    cp = _parser(dirs)
-    if cp.has_option(section, key):
-        val = cp.get(section, key)
-        return None if val == _NONE else val
-    return None
+def _read(path: str) -> configparser.ConfigParser:
+    cp = _new_parser()
+    with open(path, "r") as f:
+        cp.read_file(f)
+    return cp
+
+
+def _scheduler(name: str) -> Scheduler:
+    factories = get_scheduler_factories()
+    if name not in factories:
+        raise ValueError(f"`{name}` is not a registered scheduler. Valid scheduler names: {factories.keys()}")
+    return factories[name](session_name="_")
+
+
+def find_configs(dirs: Optional[Iterable[str]] = None) -> List[str]:
+    """Readable config files in reading order.  ``$TORCHXCONFIG`` short-circuits the directory search."""
+    explicit = os.getenv(ENV_TORCHXCONFIG)
+    if explicit is not None:
+        if not explicit:
+            return []
+        if not Path(explicit).is_file():
+            raise FileNotFoundError(f"`{ENV_TORCHXCONFIG}={explicit}` does not exist or is not a file.")
+        return [str(Path(explicit))]
+    found = []
+    for d in (list(dirs) if dirs else DEFAULT_CONFIG_DIRS):
+        candidate = Path(d) / CONFIG_FILE
+        if os.access(candidate, os.R_OK):
+            found.append(str(candidate))
+    return found
+
+
+def load(scheduler: str, f: TextIO, cfg: Dict[str, CfgVal]) -> None:
+    """Merge the ``[scheduler]`` section of the INI stream ``f`` into ``cfg`` without overriding keys that are already
+    there; literals are typed by the scheduler's runopts, unknown options are reported and skipped."""
+    cp = _new_parser()
+    cp.read_file(f)
+    if not cp.has_section(scheduler):
+        return
+    sched = _scheduler(scheduler)
+    try:
+        opts = sched.run_opts()
+    finally:
+        sched.close()
+    for name, raw in cp.items(scheduler):
+        if name in cfg:
+            continue
+        if raw == _NONE:
+            cfg[name] = None
+            continue
+        opt = opts.get(name)
+        if opt is None:
+            log.warning(f"`{name} = {raw}` was declared in the [{scheduler}] section of the config file but is not a runopt of"
+                        f" `{scheduler}` scheduler. Remove the entry from the config file to no longer see this warning")
+        elif opt.opt_type is bool:
+            cfg[name] = cp.getboolean(scheduler, name)
+        elif opt.is_type_list_of_str:
+            cfg[name] = raw.split(";")
+        elif opt.is_type_dict_of_str:
+            cfg[name] = dict(pair.split(":", 1) for pair in raw.replace(",", ";").split(";"))
+        else:
+            cfg[name] = opt.opt_type(raw)
+
+
+def apply(scheduler: str, cfg: Dict[str, CfgVal], dirs: Optional[List[str]] = None) -> None:
+    """Fill ``cfg`` IN PLACE from the config files (see the module docstring for precedence)."""
+    for path in find_configs(dirs):
+        with open(path, "r") as f:
+            load(scheduler, f, cfg)
+        log.info(f"loaded configs from {path}")
 
 
 def load_sections(prefix: str, dirs: Optional[List[str]] = None) -> Dict[str, Dict[str, str]]:
-    """All ``[prefix:*]`` sections as {name: {key: value}} (used for ``[component:dist.ddp]`` defaults)."""
-    cp = _parser(dirs)
+    """All ``[prefix:name]`` sections as ``{name: {key: raw string}}``; across files the first definition of a key wins."""
     out: Dict[str, Dict[str, str]] = {}
-    for section in cp.sections():
-        head, sep, name = section.partition(":")
-        if sep and head == prefix:
-            out[name] = {k: v for k, v in cp.items(section) if v != _NONE}
+    for path in find_configs(dirs):
+        cp = _read(path)
+        for section in cp.sections():
+            head, sep, name = section.partition(CONFIG_PREFIX_DELIM)
+            if not (sep and head == prefix and name):
+                continue
+            merged = out.setdefault(name, {})
+            for key, value in cp.items(section):
+                merged.setdefault(key, value)
     return out
 
 
-def apply(scheduler: str, cfg: Dict[str, CfgVal], dirs: Optional[List[str]] = None, opts: Optional[runopts] = None) -> None:
-    """Fill ``cfg`` IN PLACE with the ``[scheduler]`` section's values for keys the caller did not set; literals are
-    cast with the scheduler's runopts when given."""
-    cp = _parser(dirs)
-    if not cp.has_section(scheduler):
-        return
-    for key, raw in cp.items(scheduler):
-        if key in cfg or raw == _NONE:
-            continue
-        opt = opts.get(key) if opts is not None else None
-        cfg[key] = opt.cast_to_type(raw) if opt is not None else raw
+def get_configs(prefix: str, name: str, dirs: Optional[List[str]] = None) -> Dict[str, str]:
+    return load_sections(prefix, dirs).get(name, {})
 
 
-def dump(f, schedulers: Optional[List[str]] = None, required_only: bool = False) -> None:
-    """Write a template config with every scheduler's options (``torchx configure``)."""
-    from torchx_b200.schedulers import get_scheduler_factories
+def get_config(prefix: str, name: str, key: str, dirs: Optional[List[str]] = None) -> Optional[str]:
+    return get_configs(prefix, name, dirs).get(key)
 
-    cp = configparser.ConfigParser()
-    cp.optionxform = str  # type: ignore[assignment]
-    for name, factory in get_scheduler_factories().items():
-        if schedulers and name not in schedulers:
-            continue
-        sched = factory("")
+
+def _fixme_placeholder(opt: runopt, max_len: int = 60) -> str:
+    text = f"#FIXME:({get_type_name(opt.opt_type)}) {opt.help}"
+    return text if len(text) <= max_len else f"{text[:max_len]}..."
+
+
+def dump(f: TextIO, schedulers: Optional[List[str]] = None, required_only: bool = False) -> None:
+    """Write a template: one section per scheduler, optional runopts pre-filled with their defaults, required ones with a
+    ``#FIXME`` placeholder (``required_only`` drops the optional ones).  Unknown scheduler names raise ``ValueError``."""
+    cp = _new_parser()
+    for name in (schedulers or list(get_scheduler_factories())):
         try:
-            section = {k: str(o.default) for k, o in sched.run_opts() if o.is_required or not required_only}
+            sched = _scheduler(name)
+        except ModuleNotFoundError:  # a scheduler whose optional dependency is not installed
+            continue
+        try:
+            cp.add_section(name)
+            for key, opt in sched.run_opts():
+                if opt.is_required:
+                    val = _fixme_placeholder(opt)
+                elif required_only:
+                    continue
+                elif opt.is_type_list_of_str:
+                    val = ";".join(opt.default) if opt.default else _NONE  # type: ignore[arg-type]
+                elif opt.is_type_dict_of_str:
+                    val = ";".join(f"{k}:{v}" for k, v in opt.default.items()) if opt.default else _NONE  # type: ignore[union-attr]
+                else:
+                    val = f"{opt.default}"
+                cp.set(name, key, val)
         finally:
             sched.close()
-        if section:
-            cp[name] = section
-    cp.write(f)
+    cp.write(f, space_around_delimiters=True)
