@@ -14,6 +14,7 @@ import time
 from datetime import datetime
 from typing import Any, Dict, Iterable, List, Mapping, Optional, Tuple, Union
 
+from torchx_b200.runner import events
 from torchx_b200.schedulers import SchedulerFactory, get_scheduler_factories
 from torchx_b200.schedulers.api import ListAppResponse, Scheduler, Stream
 from torchx_b200.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID, TORCHX_INTERNAL_SESSION_ID
@@ -34,6 +35,22 @@ from torchx_b200.specs.finder import get_component
 from torchx_b200.util.session import get_session_id_or_create_new
 
 logger = logging.getLogger(__name__)
+
+
+def _logged(api: str):
+    """Wrap a Runner method in the (no-op by default) per-call event of runner/events."""
+
+    def deco(fn):
+        import functools
+
+        @functools.wraps(fn)
+        def wrapper(self, *args, **kwargs):
+            with events.log_event(api):
+                return fn(self, *args, **kwargs)
+
+        return wrapper
+
+    return deco
 
 
 class Runner:
@@ -92,6 +109,7 @@ class Runner:
         return opts.resolve(cfg)
 
     # -- submission -------------------------------------------------------------------------------------------------
+    @_logged("dryrun_component")
     def dryrun_component(self, component: str, component_args: Union[List[str], Dict[str, Any]], scheduler: str,
                          cfg: Optional[Mapping[str, CfgVal]] = None, workspace: Optional[object] = None,
                          parent_run_id: Optional[str] = None) -> AppDryRunInfo:
@@ -101,11 +119,13 @@ class Runner:
         app = materialize_appdef(comp.fn, cli_args, self._component_defaults.get(component), json_args)
         return self.dryrun(app, scheduler, cfg=cfg, workspace=workspace, parent_run_id=parent_run_id)
 
+    @_logged("run_component")
     def run_component(self, component: str, component_args: Union[List[str], Dict[str, Any]], scheduler: str,
                       cfg: Optional[Mapping[str, CfgVal]] = None, workspace: Optional[object] = None,
                       parent_run_id: Optional[str] = None) -> AppHandle:
         return self.schedule(self.dryrun_component(component, component_args, scheduler, cfg, workspace, parent_run_id))
 
+    @_logged("dryrun")
     def dryrun(self, app: AppDef, scheduler: str, cfg: Optional[Mapping[str, CfgVal]] = None, workspace: Optional[object] = None,
                parent_run_id: Optional[str] = None) -> AppDryRunInfo:
         if not app.roles:
@@ -130,6 +150,7 @@ class Runner:
         info._scheduler = scheduler
         return info
 
+    @_logged("schedule")
     def schedule(self, dryrun_info: AppDryRunInfo) -> AppHandle:
         scheduler = dryrun_info._scheduler
         assert scheduler is not None, "dryrun_info was not produced by Runner.dryrun"
@@ -139,12 +160,14 @@ class Runner:
             self._apps[handle] = dryrun_info._app
         return handle
 
+    @_logged("run")
     def run(self, app: AppDef, scheduler: str, cfg: Optional[Mapping[str, CfgVal]] = None, workspace: Optional[object] = None,
             parent_run_id: Optional[str] = None, *, dryrun: bool = False) -> Union[AppHandle, AppDryRunInfo]:
         info = self.dryrun(app, scheduler, cfg=cfg, workspace=workspace, parent_run_id=parent_run_id)
         return info if dryrun else self.schedule(info)
 
     # -- monitoring -------------------------------------------------------------------------------------------------
+    @_logged("status")
     def status(self, app_handle: AppHandle) -> Optional[AppStatus]:
         sched, _, app_id = self._scheduler_app_id(app_handle)
         desc = sched.describe(app_id)
@@ -154,6 +177,7 @@ class Runner:
         return AppStatus(desc.state, desc.num_restarts, msg=desc.msg, structured_error_msg=desc.structured_error_msg,
                          roles=desc.roles_statuses, ui_url=desc.ui_url)
 
+    @_logged("wait")
     def wait(self, app_handle: AppHandle, wait_interval: float = 10) -> Optional[AppStatus]:
         while True:
             st = self.status(app_handle)
@@ -161,6 +185,7 @@ class Runner:
                 return st
             time.sleep(wait_interval)
 
+    @_logged("cancel")
     def cancel(self, app_handle: AppHandle) -> None:
         sched, _, app_id = self._scheduler_app_id(app_handle)
         st = self.status(app_handle)
@@ -169,11 +194,13 @@ class Runner:
 
     stop = cancel
 
+    @_logged("delete")
     def delete(self, app_handle: AppHandle) -> None:
         sched, _, app_id = self._scheduler_app_id(app_handle)
         if self.status(app_handle) is not None:
             sched.delete(app_id)
 
+    @_logged("describe")
     def describe(self, app_handle: AppHandle) -> Optional[AppDef]:
         sched, _, app_id = self._scheduler_app_id(app_handle)
         app = self._apps.get(app_handle)
@@ -183,6 +210,7 @@ class Runner:
                 app = AppDef(name=app_id, roles=desc.roles, metadata=desc.metadata)
         return app
 
+    @_logged("log_lines")
     def log_lines(self, app_handle: AppHandle, role_name: str, k: int = 0, regex: Optional[str] = None, since: Optional[datetime] = None,
                   until: Optional[datetime] = None, should_tail: bool = False, streams: Optional[Stream] = None) -> Iterable[str]:
         """Lines keep their trailing newline; ``k`` is the replica (node) index, not the worker rank."""
@@ -191,6 +219,7 @@ class Runner:
             raise UnknownAppException(app_handle)
         return sched.log_iter(app_id, role_name, k, regex, since, until, should_tail, streams=streams)
 
+    @_logged("list")
     def list(self, scheduler: str, cfg: Optional[Mapping[str, CfgVal]] = None) -> List[ListAppResponse]:
         apps = self._scheduler(scheduler).list(cfg)
         for a in apps:
