@@ -37,7 +37,9 @@ class _Ctx:
 
 @contextmanager
 def log_event(api: str, scheduler: Optional[str] = None, app_id: Optional[str] = None, **kwargs: object) -> Iterator[_Ctx]:
-    ev = TorchxEvent(api=api, scheduler=scheduler or "", app_id=app_id)
+    from torchx_b200.util.session import get_session_id_or_create_new
+
+    ev = TorchxEvent(session=get_session_id_or_create_new(), api=api, scheduler=scheduler or "", app_id=app_id)
     t0 = time.perf_counter_ns()
     try:
         yield _Ctx(ev)
