@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 #define B2_MAX_WORLD 8 /* one NVSwitch domain: 8 x B200 */
 
 /* ---- return codes ---------------------------------------------------------------- */
@@ -50,6 +50,7 @@ extern "C" {
 #define B2_ETIMEOUT (-4) /* rendezvous or an in-kernel peer wait timed out */
 #define B2_ENOPEER (-5)  /* two ranks' devices cannot reach each other over P2P */
 #define B2_ESTATE (-6)   /* communicator is poisoned by an earlier failure */
+#define B2_ENOTSUP (-7)  /* the requested algorithm needs a capability this communicator lacks (b2_comm_caps) */
 
 /* ---- element / wire formats ------------------------------------------------------ */
 /* The arithmetic of every mode is fixed so results are bit-reproducible run to run and
@@ -62,9 +63,16 @@ extern "C" {
 
 /* ---- algorithm selection --------------------------------------------------------- */
 #define B2_ALGO_AUTO 0
-#define B2_ALGO_ONESHOT 1 /* push whole message to every peer, one flag barrier, reduce locally   */
-#define B2_ALGO_TWOSHOT 2 /* push-scatter (fused cast) -> reduce own slice -> pull-gather (fused cast) */
-#define B2_ALGO_TWOSHOT_PULL 3 /* compress into own stage -> pull-reduce own slice -> pull-gather: no peer stores */
+#define B2_ALGO_ONESHOT 1      /* push whole message to every peer, one flag barrier, reduce locally                  */
+#define B2_ALGO_TWOSHOT 2      /* push-scatter (fused cast) -> reduce own slice -> pull-gather (fused cast), one pass */
+#define B2_ALGO_TWOSHOT_PIPE 3 /* the same three phases as warp-specialised roles pipelined over K chunks             */
+#define B2_ALGO_NVLS 4         /* cast -> multimem.ld_reduce + multimem.st through the NVSwitch -> widen, pipelined;
+                                  needs B2_CAP_MULTICAST.  The switch sums the W contributions with fp32 accumulation
+                                  and rounds once; its summation order is the switch's, see DESIGN.md 2.4              */
+
+/* ---- capabilities (b2_comm_caps) -------------------------------------------------- */
+#define B2_CAP_VMM 1       /* arena is a CUDA VMM allocation shared by file descriptor (else cudaMalloc + CUDA IPC) */
+#define B2_CAP_MULTICAST 2 /* arena is bound into an NVSwitch multicast object on every rank: NVLS is available    */
 
 typedef struct b2_comm b2_comm_t; /* opaque */
 
@@ -99,12 +107,27 @@ int b2_comm_rank(const b2_comm_t* comm);
 int b2_comm_world(const b2_comm_t* comm);
 int b2_comm_device(const b2_comm_t* comm);
 
-/* In-kernel peer-wait timeout (default 30 s; B2_TIMEOUT_MS env overrides at create time). */
+/* Bitmask of B2_CAP_* this communicator ended up with (identical on every rank), or B2_EINVAL. */
+int b2_comm_caps(const b2_comm_t* comm);
+
+/* In-kernel peer-wait timeout (default 600 s, NCCL's default for the same situation; B2_TIMEOUT_MS env overrides at
+ * create time).  A kernel that gives up records B2_ETIMEOUT for b2_comm_status() and poisons the communicator. */
 int b2_comm_set_timeout_ms(b2_comm_t* comm, int timeout_ms);
 
 /* Upper bound on CTAs one collective may occupy (default: tuned per message size; 0 restores it).
  * Must be set identically on every rank. */
 int b2_comm_set_max_ctas(b2_comm_t* comm, int max_ctas);
+
+/*
+ * Tuning knobs of the AUTO algorithm choice and of the pipelined kernels; must be set identically on every rank.
+ *   "oneshot_max_bytes"  one-shot up to this many wire bytes           (env B2_ONESHOT_MAX_BYTES)
+ *   "pipe_min_bytes"     pipelined two-shot from this many wire bytes   (env B2_PIPE_MIN_BYTES)
+ *   "nvls_min_bytes"     NVLS from this many wire bytes                 (env B2_NVLS_MIN_BYTES)
+ *   "nvls_min_world"     NVLS from this world size                      (env B2_NVLS_MIN_WORLD)
+ *   "pipe_chunk_bytes"   target wire bytes per pipeline chunk           (env B2_PIPE_CHUNK_KB, in KiB)
+ *   "max_ctas"           same as b2_comm_set_max_ctas
+ */
+int b2_comm_set_param(b2_comm_t* comm, const char* name, long long value);
 
 /*
  * Non-blocking health check: B2_OK, or B2_ETIMEOUT if any kernel of this communicator gave up
@@ -117,10 +140,12 @@ int b2_comm_status(const b2_comm_t* comm);
 uint64_t b2_comm_launch_count(const b2_comm_t* comm);
 
 /*
- * Measurement aid (tools/sweep_allreduce.py --trace): when enabled, thread 0 of every CTA of a collective records
- * %globaltimer at its phase boundaries (8 u64 slots per CTA: start, scatter done, barrier 1 passed, reduce done,
- * barrier 2 passed, gather done).  Calling with a non-NULL `out` first copies the stamps of the most recent
- * collective for CTAs [0, max_ctas) (synchronously; call after a stream sync), then applies `enable`.
+ * Measurement aid (tools/sweep_allreduce.py --trace): when enabled, every CTA of a collective records %globaltimer at
+ * its phase boundaries, 8 u64 slots per CTA.  Single-pass kernels: start, scatter/push done, barrier 1 passed, reduce
+ * done, barrier 2 passed, gather done.  Pipelined kernels (one stamp per role group): role A start, role A done (all
+ * chunks), role B passed its first wait, role B done, role C passed its first wait, role C done.  Calling with a
+ * non-NULL `out` first copies the stamps of the most recent collective for CTAs [0, max_ctas) (synchronously; call
+ * after a stream sync), then applies `enable`.
  */
 int b2_comm_trace(b2_comm_t* comm, int enable, uint64_t* out, int max_ctas);
 

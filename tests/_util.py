@@ -54,3 +54,34 @@ def assert_bits_equal(got: np.ndarray, want: np.ndarray, what: str = "") -> None
     assert bad.size == 0, (
         f"{what}: {bad.size} of {got.size} elements differ; first at {bad[:8]}: got {gf[bad[:8]]} want {wf[bad[:8]]}"
     )
+
+
+def assert_nvls_result(got: np.ndarray, inputs: list, scale: float, mode: int, what: str = "") -> dict:
+    """The NVLS path lets the NVSwitch add the W wire contributions (fp32 accumulation, one rounding to bf16).  The
+    switch's summation ORDER is not the rank order of the P2P kernels, so the contract checked here is:
+      * wherever the exact sum of the contributions is representable in fp32 along EVERY summation order the result is
+        order-independent and must equal the rank-order oracle bit for bit (the overwhelming majority of elements);
+      * elsewhere it must equal the correctly rounded bf16 of SOME fp32 summation order: checked as within one bf16 ulp
+        of the exact (float64) sum.
+    Returns counts for reporting."""
+    want = oracle.allreduce(mode, inputs, scale)
+    contrib = [oracle.compress(mode, x, scale).astype(np.float64) for x in inputs]  # bf16-representable values
+    exact = np.sum(contrib, axis=0)
+    if got.dtype == np.uint16:
+        gf, wf = oracle.bf16_bits_to_f32(got), oracle.bf16_bits_to_f32(want)
+    else:
+        gf, wf = got.astype(np.float32), want.astype(np.float32)
+    gn, wn = np.isnan(gf), np.isnan(wf)
+    assert np.array_equal(gn, wn), f"{what}: NaN positions differ at {np.flatnonzero(gn != wn)[:8]}"
+    diff = np.flatnonzero((gf.view(np.uint32) != wf.view(np.uint32)) & ~gn)
+    if diff.size:
+        # order-independence test: every partial sum of |c_r| spans < 2^24 relative to the smallest contribution bit
+        absmax = np.max(np.abs(contrib), axis=0)[diff]
+        ulp = np.maximum(np.abs(exact[diff]), np.float64(2.0) ** -126) * 2.0 ** -7  # >= one bf16 ulp of the result
+        err = np.abs(gf[diff].astype(np.float64) - exact[diff])
+        bad = diff[(err > ulp) & np.isfinite(exact[diff])]
+        assert bad.size == 0, (
+            f"{what}: {bad.size} elements are more than one bf16 ulp from the exact sum; first at {bad[:8]}: "
+            f"got {gf[bad[:8]]} exact {exact[bad[:8]]} rank-order {wf[bad[:8]]}")
+        del absmax
+    return {"n": int(got.size), "differ_from_rank_order": int(diff.size)}

@@ -6,8 +6,6 @@ import sys
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # Exercise the TMA-staged local pass at test sizes too (the library only defaults to it from 256 MiB up).
 os.environ.setdefault("B2_LOCAL_TMA_MIN_MB", "0")
-# ... and the two-lane split of large two-shot collectives (off by default: measured no gain, see b200ddp.cu).
-os.environ.setdefault("B2_SPLIT_MIN_BYTES", str(4 << 20))
 
 # The local_cuda app registry defaults to ~/.torchx_b200: keep test runs out of the home directory.
 import tempfile  # noqa: E402

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import oracle
-from tests._util import assert_bits_equal, make_inputs
+from tests._util import assert_bits_equal, assert_nvls_result, make_inputs
 
 pytestmark = pytest.mark.gpu
 
@@ -33,8 +33,8 @@ class World:
         same_device = len(set(devices)) == 1
         for c in self.comms:
             c.set_timeout(timeout_s)
-            if same_device:  # all kernels must be co-resident on one GPU: W ranks x 2 lanes x grid <= #SMs (1 CTA per SM)
-                c.set_max_ctas(max(1, 64 // len(devices)))
+            if same_device:  # all kernels must be co-resident on one GPU: W ranks x grid <= #SMs (1 CTA per SM)
+                c.set_max_ctas(max(1, 128 // len(devices)))
 
     def run(self, fn):
         """fn(rank, comm, stream) launches that rank's work; then wait for all and check health."""
@@ -73,9 +73,17 @@ def _check_allreduce(world_obj, n, mode, algo, kind, seed, offset=0):
         host.append(h[offset:])
     scale = 1.0 / W
     world_obj.run(lambda r, c, s: c.allreduce_(tens[r], scale=scale, wire=WIRE[mode], algo=algo, stream=s))
+    what = f"W={W} n={n} mode={mode} algo={algo} kind={kind}"
+    if algo == "nvls" and kind in ("randn", "special"):
+        # the switch's summation order is its own: bit-exact wherever the sum is order-independent, <= 1 bf16 ulp elsewhere
+        stats = [assert_nvls_result(_to_host(tens[r], mode), host, scale, MODES[mode], f"{what} rank={r}") for r in range(W)]
+        for r in range(1, W):  # every rank holds the SAME bits (one reduction per element, replicated by the switch)
+            assert_bits_equal(_to_host(tens[r], mode), _to_host(tens[0], mode), f"{what}: rank {r} vs rank 0")
+        return stats[0]
     want = oracle.allreduce(MODES[mode], host, scale)
     for r in range(W):
-        assert_bits_equal(_to_host(tens[r], mode), want, f"W={W} n={n} mode={mode} algo={algo} kind={kind} rank={r}")
+        assert_bits_equal(_to_host(tens[r], mode), want, f"{what} rank={r}")
+    return None
 
 
 @pytest.mark.parametrize("mode", list(MODES))
@@ -97,7 +105,7 @@ def test_local_pass_matches_oracle(mode):
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pull"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe"])
 def test_allreduce_matches_oracle_one_device(world, mode, algo):
     w = World([0] * world)
     try:
@@ -118,23 +126,25 @@ def test_allreduce_auto_and_chunking(world):
         for n in (100, 5000, 70001, (1 << 20) + 17):
             _check_allreduce(w, n, "f32_wire_bf16", "auto", "randn", seed=n)
         _check_allreduce(w, (1 << 19) + 3, "f32", "twoshot", "randn", seed=5)
-        _check_allreduce(w, (1 << 20) + 9, "f32_wire_bf16", "twoshot_pull", "special", seed=6)
+        _check_allreduce(w, (1 << 20) + 9, "f32_wire_bf16", "twoshot_pipe", "special", seed=6)
     finally:
         w.close()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("algo", ["twoshot", "twoshot_pull", "auto"])
-def test_large_buckets_split_over_two_lanes(world, algo):
-    """>= 4 MiB on the wire: the collective runs as two concurrent half-collectives (lane 1 on an internal stream)."""
-    w = World([0] * world, stage_mb=32)
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("chunk_kib", [1, 16, 4096])
+def test_pipelined_two_shot_chunking(world, chunk_kib):
+    """The warp-specialised pipeline over K chunks: tiny chunks force K = 16 with ragged last cells, one huge chunk is the
+    K = 1 degenerate case; sizes around the cell / slice boundaries; every mode; misaligned buffers."""
+    w = World([0] * world, stage_mb=8)
     try:
-        before = w.comms[0].launches
-        _check_allreduce(w, (1 << 21) + 8 * world + 5, "f32_wire_bf16", algo, "special", seed=21)
-        # AUTO at W=2 still prefers one-shot at this size (one launch); the two-shot algorithms split
-        assert w.comms[0].launches - before == (1 if (algo == "auto" and world == 2) else 2)
-        _check_allreduce(w, (1 << 20) + 3, "f32", "twoshot", "randn", seed=22)  # 4 MiB of fp32 wire: split as well
-        _check_allreduce(w, 3000, "f32_wire_bf16", "twoshot", "randn", seed=23)  # small again: single lane, same comm
+        for c in w.comms:
+            c.set_param("pipe_chunk_bytes", chunk_kib << 10)
+        for i, n in enumerate((1, 255, 256 * world, 256 * world + 1, 8 * 32 * world * 3 - 7, 70001, (1 << 19) + 13)):
+            for mode in MODES:
+                _check_allreduce(w, n, mode, "twoshot_pipe", "special" if i % 2 else "randn", seed=100 + i)
+        _check_allreduce(w, 40961, "f32_wire_bf16", "twoshot_pipe", "randn", seed=7, offset=1)
+        _check_allreduce(w, 1 << 14, "bf16", "twoshot_pipe", "ints", seed=8, offset=3)
     finally:
         w.close()
 
@@ -145,7 +155,9 @@ def test_back_to_back_ops_reuse_staging_safely():
     W = 4
     w = World([0] * W)
     try:
-        plan = [(1000 + 37 * i, ("oneshot", "twoshot", "twoshot_pull")[i % 3]) for i in range(42)]
+        for c in w.comms:
+            c.set_param("pipe_chunk_bytes", 1 << 10)
+        plan = [(1000 + 37 * i, ("oneshot", "twoshot", "twoshot_pipe")[i % 3]) for i in range(42)]
         tens = [[None] * len(plan) for _ in range(W)]
         wants = []
         for k, (n, _) in enumerate(plan):
@@ -221,14 +233,27 @@ def test_dead_peer_times_out_instead_of_hanging():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pull"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe", "nvls", "auto"])
 def test_allreduce_across_devices(world, algo, cuda_count):
-    """Real NVLink/NVSwitch peers (skipped on a 1-GPU box)."""
+    """Real NVLink/NVSwitch peers (skipped on a 1-GPU box).  In-process worlds over distinct devices use the VMM arena and,
+    where the fabric offers it, the multicast object - the same mappings as the one-process-per-GPU path minus fd passing."""
     devs = _devices(world, cuda_count, spread=True)
     w = World(devs, stage_mb=64)
     try:
+        if algo == "nvls" and not w.comms[0].has_multicast:
+            pytest.skip("no NVSwitch multicast on this box")
+        for c in w.comms:
+            c.set_param("pipe_chunk_bytes", 64 << 10)
+            c.set_param("nvls_min_bytes", 64 << 10)   # AUTO crosses one-shot -> NVLS / pipelined inside the sizes below
+            c.set_param("pipe_min_bytes", 256 << 10)
+        nvlsish = algo == "nvls" or (algo == "auto" and w.comms[0].has_multicast and world >= 4)
         for mode in MODES:
+            if algo == "nvls" and mode == "f32":
+                continue  # fp32-wire NVLS: summation order is the switch's for every element; covered by the probe tool
             for n in (9, 4099, (1 << 20) + 5):
-                _check_allreduce(w, n, mode, algo, "special", seed=n)
+                _check_allreduce(w, n, mode, algo, "ints" if nvlsish else "special", seed=n)
+            if nvlsish:
+                _check_allreduce(w, (1 << 20) + 5, mode, "nvls" if mode != "f32" else algo, "randn", seed=3)
+                _check_allreduce(w, 1 << 16, mode, algo, "onehot", seed=0)
     finally:
         w.close()

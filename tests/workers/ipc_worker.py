@@ -1,5 +1,6 @@
 """One rank of a multi-process topology (spawned by tests/test_ipc_gpu.py). Exercises the real rendezvous:
-POSIX-shm control block + CUDA-IPC arena exchange, then allreduce / broadcast / barrier through the C ABI."""
+POSIX-shm control block + arena exchange (VMM file descriptors + NVSwitch multicast where the box offers them, else
+CUDA IPC), then allreduce / broadcast / barrier through the C ABI."""
 import argparse
 import os
 import sys
@@ -29,11 +30,18 @@ def main() -> None:
     comm.set_timeout(30.0)
     comm.set_max_ctas(a.max_ctas)
     results = {}
-    for k, (algo, mode) in enumerate([("twoshot", "bf16"), ("oneshot", "bf16"), ("twoshot", "f32"), ("twoshot_pull", "bf16")]):
+    comm.set_param("pipe_chunk_bytes", 16 << 10)  # several pipeline chunks even at this message size
+    for k, (algo, mode) in enumerate([("twoshot", "bf16"), ("oneshot", "bf16"), ("twoshot", "f32"), ("twoshot_pipe", "bf16")]):
         x = make_inputs(a.world, a.n, 10 + k, "special")[a.rank]
         t = torch.from_numpy(x).to(f"cuda:{a.device}")
         comm.allreduce_(t, wire=mode, algo=algo)
         results[f"ar{k}"] = t.cpu().numpy()
+    results["caps"] = np.array([comm.caps])
+    if comm.has_multicast:  # NVLS through the multi-process multicast bring-up (fd passing, AddDevice / BindMem handshake)
+        x = make_inputs(a.world, a.n, 20, "randn")[a.rank]
+        t = torch.from_numpy(x).to(f"cuda:{a.device}")
+        comm.allreduce_(t, wire="bf16", algo="nvls")
+        results["nvls"] = t.cpu().numpy()
     b = torch.full((4097,), float(a.rank + 1), device=f"cuda:{a.device}")
     comm.broadcast_(b, root=a.world - 1)
     comm.barrier()

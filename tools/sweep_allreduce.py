@@ -1,16 +1,22 @@
-"""Allreduce bandwidth sweep (BASELINE.json config #4): the fused B200 kernel vs the reference path's NCCL,
+"""Allreduce bandwidth sweep (BASELINE.json config #4): the fused B200 kernels vs the reference path's NCCL,
 launched one process per GPU (torchrun or `torchx run -s local_cuda dist.ddp`).
 
 For each message size S (bytes of the fp32 bucket) it times, device-side with CUDA events and max over ranks:
-  ours_fused      b2_allreduce  fp32 bucket, bf16 wire, 1/W scale fused   (ONE launch)
-  ref_hook_seq    buf.to(bf16).div_(W) -> dist.all_reduce(NCCL) -> buf.copy_()   (what bf16_compress_hook runs)
-  nccl_bf16       dist.all_reduce on a bf16 tensor of the same element count (the wire-only part of the above)
+  ours[<variant>]  b2_allreduce  fp32 bucket, bf16 wire, 1/W scale fused   (ONE launch); a variant is
+                   algo[:ctas=N][:chunk=KiB], e.g. "auto", "nvls:ctas=128:chunk=1024", "twoshot_pipe:chunk=4096"
+  ref_hook_seq     buf.to(bf16).div_(W) -> dist.all_reduce(NCCL) -> buf.copy_()   (what bf16_compress_hook runs)
+  nccl_bf16        dist.all_reduce on a bf16 tensor of the same element count (the wire-only part of the above)
   ours_f32 / nccl_f32   fp32 wire variants (DDP default semantics)
 busbw = (wire bytes / t) * 2(W-1)/W, nccl-tests convention; wire bytes = 2N (bf16) or 4N (fp32).
+
+--nvlink-counters: rank 0 reads `nvidia-smi nvlink -gt d` before and after one timed loop per size and reports the
+NVLink bytes its GPU sent / received per collective (hardware counters, not a model).
 """
 import argparse
 import json
 import os
+import re
+import subprocess
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -37,17 +43,45 @@ def time_op(fn, bufs, iters, warmup, stream):
     return float(t.item())
 
 
+def nvlink_kib(gpu: int):
+    """(tx KiB, rx KiB) summed over the GPU's links from `nvidia-smi nvlink -gt d`, or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = sum(int(m) for m in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out))
+    rx = sum(int(m) for m in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out))
+    return (tx, rx) if (tx or rx) else None
+
+
+def parse_variant(v):
+    parts = v.split(":")
+    d = {"algo": parts[0], "ctas": 0, "chunk": 0}
+    for p in parts[1:]:
+        k, val = p.split("=")
+        d[k] = int(val)
+    return d
+
+
+TRACE_NAMES = {
+    "oneshot": (["push", "bar1", "reduce"], 3),
+    "twoshot": (["scatter", "bar1", "reduce", "bar2", "gather"], 5),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--min-kib", type=int, default=4)
     ap.add_argument("--max-mib", type=int, default=1024)
-    ap.add_argument("--ctas", default="0", help="comma list of max_ctas values to try for ours (0 = default)")
-    ap.add_argument("--algos", default="auto")
+    ap.add_argument("--sizes-mib", default="", help="explicit comma list of fp32 bucket sizes in MiB (replaces the power-of-two ladder)")
+    ap.add_argument("--variants", default="auto", help="';'-separated list of algo[:ctas=N][:chunk=KiB]")
     ap.add_argument("--extra-mib", default="7.82,30.04,25.04,25.32,9.27,27.04,168.27", help="DDP bucket sizes (SURVEY 8a)")
     ap.add_argument("--skip-nccl", action="store_true")
+    ap.add_argument("--skip-f32", action="store_true")
     ap.add_argument("--oneshot-max-mib", type=float, default=32.0, help="do not time the forced one-shot algorithm above this size")
     ap.add_argument("--out", default="")
-    ap.add_argument("--trace", action="store_true", help="record the per-CTA phase breakdown of one launch per size/algo")
+    ap.add_argument("--trace", action="store_true", help="record the per-CTA phase breakdown of one launch per size/variant")
+    ap.add_argument("--nvlink-counters", action="store_true")
     a = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -56,12 +90,18 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     comm = Communicator.from_env(stage_mb=int(os.environ.get("B2_STAGE_MB", "0") or 0))
     stream = torch.cuda.Stream()
-    sizes = []
-    s = a.min_kib << 10
-    while s <= a.max_mib << 20:
-        sizes.append(s)
-        s *= 2
-    sizes += [int(float(m) * (1 << 20)) // 32 * 32 for m in a.extra_mib.split(",") if m]
+    if a.sizes_mib:
+        sizes = [int(float(m) * (1 << 20)) // 32 * 32 for m in a.sizes_mib.split(",") if m]
+    else:
+        sizes = []
+        s = a.min_kib << 10
+        while s <= a.max_mib << 20:
+            sizes.append(s)
+            s *= 2
+        sizes += [int(float(m) * (1 << 20)) // 32 * 32 for m in a.extra_mib.split(",") if m]
+    variants = [parse_variant(v) for v in a.variants.split(";") if v]
+    if rank == 0:
+        print(json.dumps({"world": world, "caps": comm.caps, "has_multicast": comm.has_multicast, "variants": a.variants}), flush=True)
     rows = []
     for S in sizes:
         n = S // 4
@@ -73,7 +113,7 @@ def main():
         row = {"bytes_fp32": S, "n": n, "world": world}
         k = 2.0 * (world - 1) / world
 
-        # parity first (one fresh buffer): ours vs NCCL bf16 path
+        # parity first (one fresh buffer): ours (AUTO) vs NCCL bf16 path
         x = bufs[0].clone()
         y = bufs[0].clone()
         with torch.cuda.stream(stream):
@@ -87,34 +127,52 @@ def main():
         row["max_abs_diff_over_max_abs_vs_nccl_bf16"] = float(((x - y).abs().max() / y.abs().max().clamp_min(1e-30)).item()) if n else 0.0
         row["bit_equal_vs_nccl_bf16"] = bool(torch.equal(x, y))
 
-        for ctas in [int(v) for v in a.ctas.split(",")]:
-            comm.set_max_ctas(ctas)
-            for algo in a.algos.split(","):
-                if algo == "oneshot" and S > a.oneshot_max_mib * (1 << 20):
-                    continue
-                t = time_op(lambda b: comm.allreduce_(b, algo=algo, stream=stream), bufs, iters, warm, stream)
-                key = f"ours_fused[{algo},ctas={ctas}]"
-                row[key] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1), "hbm_alg_gbs": round(8 * n / t / 1e9, 1)}
-                if a.trace and algo != "auto":
-                    comm.trace(True)
-                    dist.barrier()
-                    comm.allreduce_(bufs[0], algo=algo, stream=stream)
-                    stream.synchronize()
-                    stamps = [st for st in comm.trace(False, read_ctas=296) if st[0]]
-                    if stamps:
-                        t0 = min(st[0] for st in stamps)
-                        last = 3 if algo == "oneshot" else 5
-                        names = {"oneshot": ["push", "bar1", "reduce"], "twoshot": ["scatter", "bar1", "reduce", "bar2", "gather"],
-                                 "twoshot_pull": ["compress", "bar1", "pull_reduce", "bar2", "gather"]}[algo]
-                        med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
+        for v in variants:
+            algo = v["algo"]
+            if algo == "oneshot" and S > a.oneshot_max_mib * (1 << 20):
+                continue
+            if algo == "nvls" and not comm.has_multicast:
+                continue
+            comm.set_max_ctas(v["ctas"])
+            comm.set_param("pipe_chunk_bytes", (v["chunk"] or 2048) << 10)
+            key = f"ours[{algo},ctas={v['ctas']},chunk={v['chunk']}]"
+            nv0 = nvlink_kib(local_rank) if (a.nvlink_counters and rank == 0) else None
+            t = time_op(lambda b: comm.allreduce_(b, algo=algo, stream=stream), bufs, iters, warm, stream)
+            row[key] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1), "frac_of_900": round(2 * n / t * k / 1e9 / 900, 4),
+                        "hbm_alg_gbs": round(8 * n / t / 1e9, 1)}
+            if nv0 is not None:
+                nv1 = nvlink_kib(local_rank)
+                if nv1 is not None:
+                    ops = iters + warm
+                    row[key]["nvlink_tx_bytes_per_op"] = round((nv1[0] - nv0[0]) * 1024 / ops)
+                    row[key]["nvlink_rx_bytes_per_op"] = round((nv1[1] - nv0[1]) * 1024 / ops)
+                    row[key]["wire_bytes_S"] = 2 * n
+            if a.trace and algo != "auto":
+                comm.trace(True)
+                dist.barrier()
+                comm.allreduce_(bufs[0], algo=algo, stream=stream)
+                stream.synchronize()
+                stamps = [st for st in comm.trace(False, read_ctas=296) if st[0]]
+                if stamps:
+                    t0 = min(st[0] for st in stamps)
+                    med = lambda xs: sorted(xs)[len(xs) // 2]  # noqa: E731
+                    if algo in TRACE_NAMES:
+                        names, last = TRACE_NAMES[algo]
                         row[key]["trace_us"] = {
                             "ctas": len(stamps), "start_spread": round((max(st[0] for st in stamps) - t0) / 1e3, 2),
                             **{nm: round(med([st[i + 1] - st[i] for st in stamps]) / 1e3, 2) for i, nm in enumerate(names)},
                             "total": round((max(st[last] for st in stamps) - t0) / 1e3, 2),
                         }
+                    else:  # pipelined kernels: one stamp per role group, all relative to the earliest CTA start
+                        rel = lambda i: round(med([st[i] - t0 for st in stamps if st[i]]) / 1e3, 2)  # noqa: E731
+                        row[key]["trace_us"] = {"ctas": len(stamps), "roleA_done": rel(1), "roleB_first_wait_passed": rel(2), "roleB_done": rel(3),
+                                                "roleC_first_wait_passed": rel(4), "roleC_done": rel(5),
+                                                "total": round((max(st[5] for st in stamps) - t0) / 1e3, 2)}
         comm.set_max_ctas(0)
-        t = time_op(lambda b: comm.allreduce_(b, wire="f32", stream=stream), bufs, iters, warm, stream)
-        row["ours_f32"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(4 * n / t * k / 1e9, 1)}
+        comm.set_param("pipe_chunk_bytes", 2048 << 10)
+        if not a.skip_f32:
+            t = time_op(lambda b: comm.allreduce_(b, wire="f32", stream=stream), bufs, iters, warm, stream)
+            row["ours_f32"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(4 * n / t * k / 1e9, 1)}
         if not a.skip_nccl:
             def hook_seq(b):
                 c = b.to(torch.bfloat16).div_(world)
@@ -127,8 +185,9 @@ def main():
             t = time_op(lambda b: dist.all_reduce(b), hb, iters, warm, stream)
             row["nccl_bf16"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1)}
             del hb
-            t = time_op(lambda b: dist.all_reduce(b), bufs, iters, warm, stream)
-            row["nccl_f32"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(4 * n / t * k / 1e9, 1)}
+            if not a.skip_f32:
+                t = time_op(lambda b: dist.all_reduce(b), bufs, iters, warm, stream)
+                row["nccl_f32"] = {"us": round(t * 1e6, 2), "busbw_gbs": round(4 * n / t * k / 1e9, 1)}
         comm.check()
         if rank == 0:
             print(json.dumps(row), flush=True)

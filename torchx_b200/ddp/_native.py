@@ -13,10 +13,11 @@ from typing import Optional
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG, "lib", "libb200ddp.so")
-SRC_PATH = os.path.join(_PKG, "csrc", "b200ddp.cu")
+SRC_DIR = os.path.join(_PKG, "csrc")
+SRC_PATH = os.path.join(SRC_DIR, "b200ddp.cu")  # the one translation unit; it includes the other files of csrc/
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG), "include")
 
-B2_ABI_VERSION = 1
+B2_ABI_VERSION = 2
 B2_MAX_WORLD = 8
 
 B2_OK = 0
@@ -26,6 +27,7 @@ B2_ESYS = -3
 B2_ETIMEOUT = -4
 B2_ENOPEER = -5
 B2_ESTATE = -6
+B2_ENOTSUP = -7
 
 B2_F32_WIRE_BF16 = 0
 B2_F32 = 1
@@ -34,7 +36,11 @@ B2_BF16 = 2
 B2_ALGO_AUTO = 0
 B2_ALGO_ONESHOT = 1
 B2_ALGO_TWOSHOT = 2
-B2_ALGO_TWOSHOT_PULL = 3
+B2_ALGO_TWOSHOT_PIPE = 3
+B2_ALGO_NVLS = 4
+
+B2_CAP_VMM = 1
+B2_CAP_MULTICAST = 2
 
 NVCC_FLAGS = [
     "-gencode",
@@ -57,8 +63,10 @@ SYMBOLS = [
     "b2_comm_rank",
     "b2_comm_world",
     "b2_comm_device",
+    "b2_comm_caps",
     "b2_comm_set_timeout_ms",
     "b2_comm_set_max_ctas",
+    "b2_comm_set_param",
     "b2_comm_status",
     "b2_comm_launch_count",
     "b2_comm_trace",
@@ -80,7 +88,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     with the repo snapshot).  nvcc cross-compiles without a GPU."""
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
     hdr = os.path.join(INCLUDE_DIR, "b200ddp.h")
-    newest = max(os.path.getmtime(SRC_PATH), os.path.getmtime(hdr))
+    sources = [hdr] + [os.path.join(SRC_DIR, f) for f in os.listdir(SRC_DIR) if f.endswith((".cu", ".cuh", ".h"))]
+    newest = max(os.path.getmtime(f) for f in sources)
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
@@ -115,13 +124,15 @@ def lib() -> ctypes.CDLL:
     L.b2_comm_create_local.argtypes = [ctypes.POINTER(vp), i, ctypes.POINTER(i), sz]
     L.b2_comm_destroy.restype = i
     L.b2_comm_destroy.argtypes = [vp]
-    for name in ("b2_comm_rank", "b2_comm_world", "b2_comm_device", "b2_comm_status"):
+    for name in ("b2_comm_rank", "b2_comm_world", "b2_comm_device", "b2_comm_status", "b2_comm_caps"):
         getattr(L, name).restype = i
         getattr(L, name).argtypes = [vp]
     L.b2_comm_set_timeout_ms.restype = i
     L.b2_comm_set_timeout_ms.argtypes = [vp, i]
     L.b2_comm_set_max_ctas.restype = i
     L.b2_comm_set_max_ctas.argtypes = [vp, i]
+    L.b2_comm_set_param.restype = i
+    L.b2_comm_set_param.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
     L.b2_comm_launch_count.restype = u64
     L.b2_comm_launch_count.argtypes = [vp]
     L.b2_comm_trace.restype = i

@@ -20,7 +20,8 @@ _MODE_FOR = {
     ("f32", "f32"): N.B2_F32,
     ("bf16", "bf16"): N.B2_BF16,
 }
-ALGOS = {"auto": N.B2_ALGO_AUTO, "oneshot": N.B2_ALGO_ONESHOT, "twoshot": N.B2_ALGO_TWOSHOT, "twoshot_pull": N.B2_ALGO_TWOSHOT_PULL}
+ALGOS = {"auto": N.B2_ALGO_AUTO, "oneshot": N.B2_ALGO_ONESHOT, "twoshot": N.B2_ALGO_TWOSHOT, "twoshot_pipe": N.B2_ALGO_TWOSHOT_PIPE,
+         "nvls": N.B2_ALGO_NVLS}
 
 
 def mode_for(tensor: torch.Tensor, wire: str = "bf16") -> int:
@@ -113,6 +114,19 @@ class Communicator:
 
     def set_max_ctas(self, n: int) -> None:
         N.check(N.lib().b2_comm_set_max_ctas(self._h, n))
+
+    def set_param(self, name: str, value: int) -> None:
+        """AUTO thresholds / pipeline chunking (include/b200ddp.h: b2_comm_set_param); same value on every rank."""
+        N.check(N.lib().b2_comm_set_param(self._h, name.encode(), int(value)))
+
+    @property
+    def caps(self) -> int:
+        return int(N.lib().b2_comm_caps(self._h))
+
+    @property
+    def has_multicast(self) -> bool:
+        """True when every rank's arena is bound into one NVSwitch multicast object (the NVLS algorithm is available)."""
+        return bool(self.caps & N.B2_CAP_MULTICAST)
 
     def check(self) -> None:
         """Raise if any kernel of this communicator timed out waiting for a peer."""
