@@ -16,6 +16,7 @@
  *                         (`buf.to(bf16).div_(W)` -> ncclAllReduce(SUM) -> `buf.copy_()`, 4 launches; here ONE fused kernel)
  *                         and `dist.all_reduce`             torchx/schedulers/test/train.py:35,
  *                                                           torchx/examples/apps/compute_world_size/module/util.py:37
+ *   b2_allreduce_gather <- the Reducer's bucket copy-in fused into the hook (reducer.cpp mark_variable_ready_dense)
  *   b2_broadcast       <- DDP init / per-forward buffer sync torch/nn/parallel/distributed.py:881-890, 2176-2243
  *   b2_barrier         <- dist.barrier()                     torchx/distributed/__init__.py:268,274,297,303
  *   b2_comm_destroy    <- dist.destroy_process_group()
@@ -139,6 +140,9 @@ int b2_comm_status(const b2_comm_t* comm);
 /* Number of kernels this communicator has launched so far (for bench.py's gpu_launches). */
 uint64_t b2_comm_launch_count(const b2_comm_t* comm);
 
+/* B2_ALGO_* of the most recent multi-rank allreduce launch of this communicator (what B2_ALGO_AUTO resolved to; 0 if none). */
+int b2_comm_last_algo(const b2_comm_t* comm);
+
 /*
  * Measurement aid (tools/sweep_allreduce.py --trace): when enabled, every CTA of a collective records %globaltimer at
  * its phase boundaries, 8 u64 slots per CTA.  Single-pass kernels: start, scatter/push done, barrier 1 passed, reduce
@@ -158,6 +162,26 @@ int b2_comm_trace(b2_comm_t* comm, int enable, uint64_t* out, int max_ctas);
  */
 int b2_allreduce(b2_comm_t* comm, void* buf, size_t n_elems, int mode, float scale, int algo,
                  void* stream);
+
+/*
+ * The same collective with the INPUT gathered straight from the per-parameter gradient tensors instead of from the
+ * bucket: replaces the Reducer's copy-in pass (torch/csrc/distributed/c10d/reducer.cpp, mark_variable_ready_dense ->
+ * bucket_view.copy_(grad); with gradient_as_bucket_view the copy still happens whenever autograd produced the gradient
+ * elsewhere, torch/nn/parallel/distributed.py:589-600) - 8 bytes per element and one multi-tensor launch per bucket.
+ *      out[i] <- round( sum_r wire( scale * segment_r(i)[i - begin] ) ),   i in [0, n_elems)
+ * `segments_dev`: DEVICE array, in bucket order and without gaps: segment k covers bucket elements [begin, end) and reads
+ * them from `src` (this rank's tensor of the bucket's dtype; dense in the bucket's element order).
+ * `block_index_dev`: DEVICE array of ceil(n_elems / 4096) entries: index of the segment containing element 4096 * j.
+ * Both arrays must stay valid until the launch has executed.  `out` is this rank's bucket.
+ */
+typedef struct b2_segment {
+  const void* src;
+  uint64_t begin;
+  uint64_t end;
+} b2_segment_t;
+
+int b2_allreduce_gather(b2_comm_t* comm, void* out, size_t n_elems, const b2_segment_t* segments_dev, int n_segments,
+                        const uint32_t* block_index_dev, int mode, float scale, int algo, void* stream);
 
 /* Broadcast `bytes` bytes at `buf` from rank `root` to every rank (bit-exact copy). */
 int b2_broadcast(b2_comm_t* comm, void* buf, size_t bytes, int root, void* stream);

@@ -257,3 +257,22 @@ def test_allreduce_across_devices(world, algo, cuda_count):
                 _check_allreduce(w, 1 << 16, mode, algo, "onehot", seed=0)
     finally:
         w.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_messages_larger_than_a_stage_across_devices(world, cuda_count):
+    """stage_mb=1: every algorithm has to cut the message into several launches that alternate between the two staging
+    buffers while the peers run skewed on real NVLink."""
+    devs = _devices(world, cuda_count, spread=True)
+    w = World(devs, stage_mb=1)
+    try:
+        for c in w.comms:
+            c.set_param("pipe_chunk_bytes", 32 << 10)
+        algos = ["twoshot", "twoshot_pipe", "oneshot"] + (["nvls"] if w.comms[0].has_multicast else [])
+        for algo in algos:
+            before = w.comms[0].launches
+            _check_allreduce(w, (3 << 20) + 17, "f32_wire_bf16", algo, "ints" if algo == "nvls" else "special", seed=5)
+            assert w.comms[0].launches - before >= 3, algo
+            _check_allreduce(w, (1 << 20) + 9, "f32" if algo != "nvls" else "bf16", algo, "ints" if algo == "nvls" else "randn", seed=6)
+    finally:
+        w.close()

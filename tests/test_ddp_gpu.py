@@ -203,3 +203,99 @@ def test_comm_hook_on_stock_ddp_world1():
     finally:
         comm.close()
         dist.destroy_process_group()
+
+
+def _convnet(seed):
+    torch.manual_seed(seed)
+    # channels_last conv weights (gradient views get channels_last strides) + sizes that are not multiples of 8
+    net = nn.Sequential(nn.Conv2d(3, 5, 3, bias=True), nn.ReLU(), nn.Conv2d(5, 7, 3), nn.ReLU(), nn.Flatten(), nn.Linear(7 * 4 * 4, 11))
+    return net.cuda().to(memory_format=torch.channels_last)
+
+
+@pytest.mark.parametrize("zero_copy", [True, False])
+def test_zero_copy_bucket_fill_equals_copy_in(zero_copy):
+    """The kernel gathers the gradients straight from the per-parameter tensors (pointer table) - same bits as copying
+    them into the bucket first; channels_last weights, ragged sizes, segment-straddling vecs."""
+    from torchx_b200.ddp import Communicator, DistributedDataParallel
+
+    W = 2
+    comms = Communicator.create_local([0] * W, stage_mb=8)
+    try:
+        streams = [torch.cuda.Stream() for _ in range(W)]
+        ddps = []
+        for r in range(W):
+            comms[r].set_timeout(20.0)
+            comms[r].set_max_ctas(4)
+            with torch.cuda.stream(streams[r]):
+                ddps.append(DistributedDataParallel(_convnet(0), comms[r], bucket_cap_mb=0.002, first_bucket_mb=0.0005, zero_copy=zero_copy))
+        torch.cuda.synchronize()
+        assert len(ddps[0].buckets) >= 2
+        for step in range(3):
+            xs = [torch.randn(4, 3, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(7 * step + r)).contiguous(memory_format=torch.channels_last) for r in range(W)]
+            local = []
+            for r in range(W):
+                twin = _convnet(0)
+                twin(xs[r]).square().mean().backward()
+                local.append(_flat_grads(twin))
+            for r in range(W):
+                with torch.cuda.stream(streams[r]):
+                    ddps[r].zero_grad(set_to_none=(step != 1))  # step 1: grads stay bucket views and accumulate in place
+                    ddps[r](xs[r]).square().mean().backward()
+            torch.cuda.synchronize()
+            for c in comms:
+                c.check()
+            want = oracle.allreduce(oracle.B2O_F32_WIRE_BF16, local, 1.0 / W)
+            for r in range(W):
+                assert_bits_equal(_flat_grads(ddps[r].module), want, f"step {step} rank {r}")
+        if zero_copy:
+            assert ddps[0].gathered_buckets > 0 and ddps[0].copied_in_buckets == 0
+        else:
+            assert ddps[0].gathered_buckets == 0
+    finally:
+        for c in comms:
+            c.close()
+
+
+def test_state_dict_is_module_prefixed_like_torch_ddp_and_backward_failure_recovers():
+    from torchx_b200.ddp import Communicator, DistributedDataParallel
+
+    class Boom(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t):
+            return t.clone()
+
+        @staticmethod
+        def backward(ctx, g):
+            raise RuntimeError("boom")
+
+    class Mid(nn.Module):
+        boom = False
+
+        def forward(self, t):
+            return Boom.apply(t) if self.boom else t
+
+    def net():
+        torch.manual_seed(0)
+        return nn.Sequential(nn.Linear(64, 32), nn.ReLU(), Mid(), nn.Linear(32, 8)).cuda()
+
+    comm = Communicator.create(0, 1, 0, "/unused")
+    try:
+        d = DistributedDataParallel(net(), comm, bucket_cap_mb=0.001, first_bucket_mb=0.0005)
+        keys = list(d.state_dict().keys())
+        assert keys and all(k.startswith("module.") for k in keys)  # what torch DDP checkpoints look like
+        d.load_state_dict(d.state_dict())
+        x = torch.randn(4, 64, device="cuda")
+        d.module[2].boom = True
+        with pytest.raises(RuntimeError, match="boom"):
+            # the last layer's gradients are counted in, then backward dies: the engine drops the queued callback
+            d(x).square().mean().backward()
+        d.module[2].boom = False
+        d.zero_grad(set_to_none=True)
+        d(x).square().mean().backward()  # the next iteration starts from clean reducer state
+        torch.cuda.synchronize()
+        twin = net()
+        twin(x).square().mean().backward()
+        want = oracle.allreduce(oracle.B2O_F32_WIRE_BF16, [_flat_grads(twin)], 1.0)
+        assert_bits_equal(_flat_grads(d.module), want, "after a failed backward")
+    finally:
+        comm.close()

@@ -82,6 +82,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--trace", action="store_true", help="record the per-CTA phase breakdown of one launch per size/variant")
     ap.add_argument("--nvlink-counters", action="store_true")
+    ap.add_argument("--check-variants", action="store_true", help="compare EVERY variant's result with the NCCL hook sequence (count / first index of differing elements)")
     a = ap.parse_args()
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -136,10 +137,23 @@ def main():
             comm.set_max_ctas(v["ctas"])
             comm.set_param("pipe_chunk_bytes", (v["chunk"] or 2048) << 10)
             key = f"ours[{algo},ctas={v['ctas']},chunk={v['chunk']}]"
+            chk = None
+            if a.check_variants:
+                xv = bufs[0].clone()
+                with torch.cuda.stream(stream):
+                    comm.allreduce_(xv, algo=algo, stream=stream)
+                stream.synchronize()
+                comm.check()
+                d = (xv.view(torch.int32) != y.view(torch.int32)).nonzero()
+                chk = {"n_diff": int(d.numel()), "first_diff": int(d[0].item()) if d.numel() else -1, "last_diff": int(d[-1].item()) if d.numel() else -1,
+                       "max_abs_diff_over_max_abs": float(((xv - y).abs().max() / y.abs().max().clamp_min(1e-30)).item()), "ran": comm.last_algo}
+                del xv, d
             nv0 = nvlink_kib(local_rank) if (a.nvlink_counters and rank == 0) else None
             t = time_op(lambda b: comm.allreduce_(b, algo=algo, stream=stream), bufs, iters, warm, stream)
             row[key] = {"us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1), "frac_of_900": round(2 * n / t * k / 1e9 / 900, 4),
                         "hbm_alg_gbs": round(8 * n / t / 1e9, 1)}
+            if chk is not None:
+                row[key]["vs_nccl_hook"] = chk
             if nv0 is not None:
                 nv1 = nvlink_kib(local_rank)
                 if nv1 is not None:

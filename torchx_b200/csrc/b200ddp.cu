@@ -149,6 +149,7 @@ struct b2_comm {
   int nvls_min_world = 4;             // AUTO: NVLS only pays once (1 + 1/W) < 2 (W-1)/W, i.e. W >= 4
   size_t pipe_chunk_bytes = 0;        // target wire bytes of one pipeline chunk (per rank)
   uint64_t launches = 0;
+  int last_algo = 0;                  // B2_ALGO_* of the most recent allreduce launch (what AUTO picked)
   ShmBlock* shm = nullptr;
   std::string shm_path;
 };
@@ -308,39 +309,39 @@ PipePlan plan_pipe(const b2_comm* c, unsigned long long Ls, size_t wire_bytes) {
 }
 
 template <int MODE, int W>
-cudaError_t launch_oneshot(const CommDev& d, int grid, void* buf, unsigned long long n, float scale,
+cudaError_t launch_oneshot(const CommDev& d, const Src& src, int grid, void* buf, unsigned long long n, float scale,
                            cudaStream_t s) {
-  k_oneshot<MODE, W><<<grid, kThreads, 0, s>>>(d, buf, n, scale);
+  k_oneshot<MODE, W><<<grid, kThreads, 0, s>>>(d, src, buf, n, scale);
   return cudaGetLastError();
 }
 template <int MODE, int W>
-cudaError_t launch_twoshot(const CommDev& d, int grid, void* buf, unsigned long long n, float scale,
+cudaError_t launch_twoshot(const CommDev& d, const Src& src, int grid, void* buf, unsigned long long n, float scale,
                            cudaStream_t s) {
-  k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(d, buf, n, scale);
+  k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(d, src, buf, n, scale);
   return cudaGetLastError();
 }
 template <int MODE, int W, int ALG>
-cudaError_t launch_pipe(const CommDev& d, const PipePlan& p, void* buf, unsigned long long n, float scale,
+cudaError_t launch_pipe(const CommDev& d, const Src& src, const PipePlan& p, void* buf, unsigned long long n, float scale,
                         cudaStream_t s) {
-  k_pipe<MODE, W, ALG><<<p.grid, kThreads, 0, s>>>(d, buf, n, scale, p.K, p.cell);
+  k_pipe<MODE, W, ALG><<<p.grid, kThreads, 0, s>>>(d, src, buf, n, scale, p.K, p.cell);
   return cudaGetLastError();
 }
 
 // kind: one of B2_ALGO_ONESHOT / TWOSHOT / TWOSHOT_PIPE / NVLS
 template <int MODE>
-cudaError_t launch_by_world(const CommDev& d, int kind, int grid, const PipePlan& p, void* buf, unsigned long long n,
-                            float scale, cudaStream_t s) {
+cudaError_t launch_by_world(const CommDev& d, const Src& src, int kind, int grid, const PipePlan& p, void* buf,
+                            unsigned long long n, float scale, cudaStream_t s) {
 #define B2_CASE(Wv)                                                                                  \
   case Wv:                                                                                           \
     switch (kind) {                                                                                  \
       case B2_ALGO_ONESHOT:                                                                          \
-        return launch_oneshot<MODE, Wv>(d, grid, buf, n, scale, s);                                  \
+        return launch_oneshot<MODE, Wv>(d, src, grid, buf, n, scale, s);                                  \
       case B2_ALGO_TWOSHOT:                                                                          \
-        return launch_twoshot<MODE, Wv>(d, grid, buf, n, scale, s);                                  \
+        return launch_twoshot<MODE, Wv>(d, src, grid, buf, n, scale, s);                                  \
       case B2_ALGO_TWOSHOT_PIPE:                                                                     \
-        return launch_pipe<MODE, Wv, pl::kP2p>(d, p, buf, n, scale, s);                            \
+        return launch_pipe<MODE, Wv, pl::kP2p>(d, src, p, buf, n, scale, s);                            \
       default:                                                                                       \
-        return launch_pipe<MODE, Wv, pl::kNvls>(d, p, buf, n, scale, s);                           \
+        return launch_pipe<MODE, Wv, pl::kNvls>(d, src, p, buf, n, scale, s);                           \
     }
   switch (d.world) {
     B2_CASE(2)
@@ -357,7 +358,7 @@ cudaError_t launch_by_world(const CommDev& d, int kind, int grid, const PipePlan
 }
 
 template <int MODE>
-cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStream_t s) {
+cudaError_t launch_local(const Src& src, void* buf, unsigned long long n, float scale, cudaStream_t s) {
   // TMA-staged path for 16 B-aligned buckets.  Measured on B200 (profiles/r01_local_pass_tma_vs_plain.jsonl): the ring
   // needs several tiles per CTA to pay for its prologue - slower than the plain kernel below 25 MiB, equal to 168 MiB,
   // ahead from 512 MiB - so it is the default from 256 MiB up.  B2_LOCAL_TMA_MIN_MB moves the threshold (0 = always
@@ -365,7 +366,7 @@ cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStrea
   static const bool use_tma = env_size("B2_LOCAL_TMA", 1) != 0;
   static const unsigned long long tma_min = env_size("B2_LOCAL_TMA_MIN_MB", 256) << 20;
   const unsigned long long nbytes = n * (MODE == B2_BF16 ? 2 : 4);
-  if (use_tma && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20) && nbytes >= tma_min) {
+  if (use_tma && src.segs == nullptr && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20) && nbytes >= tma_min) {
     const unsigned long long ntiles = nbytes / tma::kTileBytes;
     unsigned long long g = ntiles < 148ull * 2 ? ntiles : 148ull * 2;  // persistent: 2 CTAs (2 x 64 KiB rings) per SM
     constexpr int kSmem = tma::kStages * tma::kTileBytes;
@@ -384,20 +385,43 @@ cudaError_t launch_local(void* buf, unsigned long long n, float scale, cudaStrea
   unsigned long long g = (V + kThreads * 4ull - 1) / (kThreads * 4ull);
   if (g < 1) g = 1;
   if (g > 148ull * 4) g = 148ull * 4;  // 4 resident CTAs per SM keep ~64 KiB of loads in flight per SM
-  k_local_pass<MODE><<<static_cast<int>(g), kThreads, 0, s>>>(buf, n, scale);
+  k_local_pass<MODE><<<static_cast<int>(g), kThreads, 0, s>>>(src, buf, n, scale);
   return cudaGetLastError();
 }
 
-cudaError_t launch_mode(const CommDev& d, int mode, int kind, int grid, const PipePlan& p, void* buf,
+cudaError_t launch_mode(const CommDev& d, const Src& src, int mode, int kind, int grid, const PipePlan& p, void* buf,
                         unsigned long long n, float scale, cudaStream_t s) {
   switch (mode) {
     case B2_F32_WIRE_BF16:
-      return launch_by_world<B2_F32_WIRE_BF16>(d, kind, grid, p, buf, n, scale, s);
+      return launch_by_world<B2_F32_WIRE_BF16>(d, src, kind, grid, p, buf, n, scale, s);
     case B2_F32:
-      return launch_by_world<B2_F32>(d, kind, grid, p, buf, n, scale, s);
+      return launch_by_world<B2_F32>(d, src, kind, grid, p, buf, n, scale, s);
     default:
-      return launch_by_world<B2_BF16>(d, kind, grid, p, buf, n, scale, s);
+      return launch_by_world<B2_BF16>(d, src, kind, grid, p, buf, n, scale, s);
   }
+}
+
+int local_pass_impl(const Src& src, void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
+  if (n_elems == 0) return B2_OK;
+  if (!buf) return fail(B2_EINVAL, "b2_local_pass: null buffer");
+  DeviceGuard g(device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  switch (mode) {
+    case B2_F32_WIRE_BF16:
+      e = launch_local<B2_F32_WIRE_BF16>(src, buf, n_elems, scale, s);
+      break;
+    case B2_F32:
+      e = launch_local<B2_F32>(src, buf, n_elems, scale, s);
+      break;
+    case B2_BF16:
+      e = launch_local<B2_BF16>(src, buf, n_elems, scale, s);
+      break;
+    default:
+      return fail(B2_EINVAL, "unknown mode %d", mode);
+  }
+  if (e != cudaSuccess) return fail(B2_ECUDA, "k_local_pass launch: %s", cudaGetErrorString(e));
+  return B2_OK;
 }
 
 size_t elem_bytes(int mode) { return mode == B2_BF16 ? 2 : 4; }
@@ -895,6 +919,8 @@ int b2_comm_status(const b2_comm_t* c) {
 
 uint64_t b2_comm_launch_count(const b2_comm_t* c) { return c ? c->launches : 0; }
 
+int b2_comm_last_algo(const b2_comm_t* c) { return c ? c->last_algo : B2_EINVAL; }
+
 int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
   if (!c) return fail(B2_EINVAL, "null communicator");
   DeviceGuard g(c->device);
@@ -909,29 +935,10 @@ int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
 }
 
 int b2_local_pass(void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
-  if (n_elems == 0) return B2_OK;
-  if (!buf) return fail(B2_EINVAL, "b2_local_pass: null buffer");
-  DeviceGuard g(device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e;
-  switch (mode) {
-    case B2_F32_WIRE_BF16:
-      e = launch_local<B2_F32_WIRE_BF16>(buf, n_elems, scale, s);
-      break;
-    case B2_F32:
-      e = launch_local<B2_F32>(buf, n_elems, scale, s);
-      break;
-    case B2_BF16:
-      e = launch_local<B2_BF16>(buf, n_elems, scale, s);
-      break;
-    default:
-      return fail(B2_EINVAL, "unknown mode %d", mode);
-  }
-  if (e != cudaSuccess) return fail(B2_ECUDA, "k_local_pass launch: %s", cudaGetErrorString(e));
-  return B2_OK;
+  return local_pass_impl(Src{nullptr, nullptr, 0}, buf, n_elems, mode, scale, device, stream);
 }
 
-int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
+static int allreduce_impl(b2_comm_t* c, Src src, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
   if (!c) return fail(B2_EINVAL, "null communicator");
   if (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16)
     return fail(B2_EINVAL, "unknown mode %d", mode);
@@ -944,8 +951,8 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
     return fail(B2_ESTATE, "communicator poisoned by an earlier peer-wait timeout");
   const int W = c->d.world;
   if (W == 1) {
-    if (mode == B2_F32 && scale == 1.0f) return B2_OK;  // identity
-    int rc = b2_local_pass(buf, n_elems, mode, scale, c->device, stream);
+    if (mode == B2_F32 && scale == 1.0f && src.segs == nullptr) return B2_OK;  // identity
+    int rc = local_pass_impl(src, buf, n_elems, mode, scale, c->device, stream);
     if (rc == B2_OK) c->launches++;
     return rc;
   }
@@ -982,13 +989,28 @@ int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale,
     const unsigned long long Ls = (V + W - 1) / W;
     const PipePlan plan = plan_pipe(c, Ls, V * wvb);
     const int grid = grid_for(c, oneshot ? V : Ls, U);
-    const cudaError_t e = launch_mode(c->d, mode, kind, grid, plan, p, n, scale, s);
+    const cudaError_t e = launch_mode(c->d, src, mode, kind, grid, plan, p, n, scale, s);
     if (e != cudaSuccess) return fail(B2_ECUDA, "allreduce kernel launch: %s", cudaGetErrorString(e));
     c->launches++;
+    c->last_algo = kind;
     p += n * elem_bytes(mode);
+    src.off += n;
     left -= n;
   }
   return B2_OK;
+}
+
+int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
+  return allreduce_impl(c, Src{nullptr, nullptr, 0}, buf, n_elems, mode, scale, algo, stream);
+}
+
+int b2_allreduce_gather(b2_comm_t* c, void* out, size_t n_elems, const b2_segment_t* segments_dev, int n_segments,
+                        const uint32_t* block_index_dev, int mode, float scale, int algo, void* stream) {
+  if (n_elems > 0 && (!segments_dev || n_segments <= 0 || !block_index_dev))
+    return fail(B2_EINVAL, "b2_allreduce_gather: segment table / block index missing");
+  static_assert(sizeof(b2_segment_t) == sizeof(Seg), "ABI segment layout");
+  return allreduce_impl(c, Src{reinterpret_cast<const Seg*>(segments_dev), block_index_dev, 0}, out, n_elems, mode, scale,
+                        algo, stream);
 }
 
 int b2_broadcast(b2_comm_t* c, void* buf, size_t bytes, int root, void* stream) {

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 // ------------------------------------------------------------------------------------------------
 // constants shared by host and device
 // ------------------------------------------------------------------------------------------------
@@ -53,6 +55,21 @@ struct CommDev {
                                     //   the NVLS path uses regions 0..W-1 as ONE contiguous message-sized buffer
   unsigned long long* trace;        // optional (b2_comm_trace): per-CTA globaltimer stamps of the LAST collective,
                                     // 8 slots per CTA (see include/b200ddp.h)
+};
+
+// Where a collective reads its INPUT from.  segs == nullptr: the bucket itself (in place).  Otherwise the bucket is only
+// the OUTPUT and the input is gathered straight from the per-parameter gradient tensors ("zero-copy bucket fill": the
+// Reducer's copy-in pass, torch/csrc/distributed/c10d/reducer.cpp mark_variable_ready_dense, disappears into the
+// first phase of the allreduce):  segs[i] = {device pointer, first bucket element, one-past-last bucket element} in
+// bucket order, covering [0, n) without gaps;  blk[e >> 12] = index of the segment holding bucket element (e & ~4095).
+struct Seg {
+  const void* src;
+  unsigned long long begin, end;
+};
+struct Src {
+  const Seg* segs;
+  const uint32_t* blk;
+  unsigned long long off;  // bucket element index of this launch's element 0 (messages larger than a stage are cut up)
 };
 
 }  // namespace
@@ -346,6 +363,51 @@ __device__ __forceinline__ void store_out(void* buf, unsigned long long e, unsig
 template <int MODE>
 __device__ __forceinline__ bool buf_aligned(const void* buf) {
   return (reinterpret_cast<uintptr_t>(buf) & (MODE == B2_BF16 ? 15u : 31u)) == 0;
+}
+
+// One input vec (elements [e, e + 8) of this launch) from wherever `src` says the input lives.
+template <int MODE>
+__device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned long long e, unsigned long long n,
+                                       bool aligned) {
+  if (src.segs == nullptr) return load_in<MODE>(buf, e, n, aligned);
+  using Elem = typename std::conditional<MODE == B2_BF16, uint16_t, float>::type;
+  const unsigned long long ge = e + src.off;  // bucket coordinates
+  uint32_t s = __ldg(src.blk + (ge >> 12));
+  while (ge >= __ldg(&src.segs[s].end)) ++s;
+  const Elem* base = static_cast<const Elem*>(src.segs[s].src);
+  const unsigned long long sb = __ldg(&src.segs[s].begin), se = __ldg(&src.segs[s].end);
+  const Elem* p = base + (ge - sb);
+  F8 x;
+  if (e + 8 <= n && ge + 8 <= se && (reinterpret_cast<uintptr_t>(p) & (MODE == B2_BF16 ? 15u : 31u)) == 0) {
+    if constexpr (MODE == B2_BF16) {
+      Wire<B2_BF16> w;
+      w.q = ldg_u4(p);
+      x = widen<B2_BF16>(w);
+    } else {
+      x = ldg_f8(p);
+    }
+  } else {  // the vec straddles parameters, is not 32 B-aligned in its tensor, or is the ragged tail
+    unsigned long long cur_b = sb, cur_e = se;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float v = 0.f;
+      if (e + i < n) {
+        const unsigned long long g = ge + i;
+        while (g >= cur_e) {
+          ++s;
+          base = static_cast<const Elem*>(src.segs[s].src);
+          cur_b = __ldg(&src.segs[s].begin);
+          cur_e = __ldg(&src.segs[s].end);
+        }
+        if constexpr (MODE == B2_BF16)
+          v = __uint_as_float(static_cast<uint32_t>(base[g - cur_b]) << 16);
+        else
+          v = base[g - cur_b];
+      }
+      x.v[i] = v;
+    }
+  }
+  return x;
 }
 
 // peer[jj] for a RUNTIME jj without putting the parameter block into local memory (select chain)

@@ -19,9 +19,13 @@
 //     B reduce : wait X1[k]; sum recv[0..W-1] of my slice in rank order (fp32), round once -> "reduced" -> signal X2[k]
 //     C gather : wait X2[k]; LOAD slice j from rank j's "reduced", widen, write my bucket
 //
-// A role group signals with  bar.sync(group) -> st.release.sys(flag)  by its first W threads and waits with
-// ld.acquire.sys(flag) -> bar.sync(group); the release fence therefore only ever drains ONE chunk of one role's stores
-// while the other two roles keep the memory system busy.  Chunk (k, b) = vecs [(k*g + b) * cell, +cell) of every slice
+// Signalling is DECOUPLED from data movement.  A release (MEMBAR.SYS: drain of the outstanding stores, ~8 us after a burst
+// of NVLink stores) executed by a data warp stalls that warp and, at the next group barrier, its whole role - measured on
+// 2xB200: ~9 us per chunk, the pipelined kernel SLOWER than the single-pass one (profiles/r02_session_a_w2.md).  So roles A
+// and B each own one SIGNALLER warp that moves no data: the data warps finish chunk k with a barrier among themselves and a
+// shared-memory mailbox store (st.release.cta), and carry on with chunk k+1; the signaller polls the mailbox
+// (ld.acquire.cta) and publishes chunk k to every rank with st.release.sys.  Waiting stays with the data warps
+// (ld.acquire.sys by their first W threads, then the group barrier): an acquire drains nothing.  Chunk (k, b) = vecs [(k*g + b) * cell, +cell) of every slice
 // (g = grid size): chunk-major, so the bytes of one pipeline step are contiguous bands of each slice, and CTA b of every
 // rank touches exactly the same vec indices - the only cross-rank dependencies are between equal CTA indices, so neither
 // a grid-wide sync nor co-residency of a rank's own CTAs is needed.
@@ -37,13 +41,23 @@ namespace pl {
 
 enum { kNvls = 0, kP2p = 1 };
 
-// role group sizes (threads): A = cast/scatter, B = move/reduce, C = widen/gather
-constexpr int kA = 192, kB = 128, kC = 192;
-static_assert(kA + kB + kC == kThreads, "role groups must tile the CTA");
-static_assert(kA % 32 == 0 && kB % 32 == 0 && kC % 32 == 0, "role groups are whole warps");
+// Warp roles (threads): A = cast/scatter (kAD data threads + one signaller warp), B = move/reduce (kBD + one signaller
+// warp), C = widen/gather.
+constexpr int kAD = 160, kBD = 96, kCD = 192, kSig = 32;
+constexpr int kA0 = 0, kAS = kA0 + kAD, kB0 = kAS + kSig, kBS = kB0 + kBD, kC0 = kBS + kSig;
+static_assert(kC0 + kCD == kThreads, "roles must tile the CTA");
+static_assert(kAD % 32 == 0 && kBD % 32 == 0 && kCD % 32 == 0, "roles are whole warps");
 
 __device__ __forceinline__ void group_sync(int id, int count) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mail_post(uint32_t* box, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(box))), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t mail_peek(const uint32_t* box) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(static_cast<uint32_t>(__cvta_generic_to_shared(box))) : "memory");
+  return v;
 }
 
 __device__ __forceinline__ uint32_t* flag_slot(uint8_t* arena, const CommDev& c, int kind, int k) {
@@ -51,11 +65,27 @@ __device__ __forceinline__ uint32_t* flag_slot(uint8_t* arena, const CommDev& c,
   return reinterpret_cast<uint32_t*>(arena + c.pflag_off + idx * kFlagSlotBytes);
 }
 
-// The `count` threads of role group `id` have issued their stores for chunk k: publish `seq` in every rank's slot.
-// Thread t (< world) pairs with rank (rank + t) % world and writes word [my rank] of that rank's slot.
-__device__ __forceinline__ void group_signal(const CommDev& c, int id, int count, int t, int kind, int k, uint32_t seq) {
-  group_sync(id, count);  // every store of the group is ordered before the release below
-  if (t < c.world) dev::st_release_sys(flag_slot(dev::peer_sel(c, t), c, kind, k) + c.rank, seq);
+// Data side: the `count` data threads of a role have issued their stores for chunk k.
+__device__ __forceinline__ void chunk_done(int id, int count, int t, uint32_t* box, int k) {
+  group_sync(id, count);                                  // every data thread's stores are ordered before the post below
+  if (t == 0) mail_post(box, static_cast<uint32_t>(k + 1));
+}
+// Signaller warp of a role: publish chunks 0..nk-1 of `kind` to every rank as the data warps complete them.
+// Lane l (< world) pairs with rank (rank + l) % world and writes word [my rank] of that rank's slot.
+__device__ __forceinline__ void signaller(const CommDev& c, int lane, const uint32_t* box, int kind, int nk, uint32_t seq) {
+  for (int k = 0; k < nk; ++k) {
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
+    while (mail_peek(box) < static_cast<uint32_t>(k + 1)) {  // chunk k not finished by the data warps yet
+      if ((++spins & 1023u) == 0) {
+        const unsigned long long now = dev::globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > c.timeout_ns) break;  // the data warps are stuck behind a dead peer: they report it themselves
+      }
+    }
+    __syncwarp();
+    if (lane < c.world) dev::st_release_sys(flag_slot(dev::peer_sel(c, lane), c, kind, k) + c.rank, seq);
+  }
 }
 // Wait until every rank has published `seq` for (kind, k): thread t (< world) polls word [t] of my own slot.
 __device__ __forceinline__ void group_wait(const CommDev& c, int id, int count, int t, int kind, int k, uint32_t seq) {
@@ -67,11 +97,12 @@ __device__ __forceinline__ void group_wait(const CommDev& c, int id, int count, 
 
 template <int MODE, int W, int ALG>
 __global__ void __launch_bounds__(kThreads, 1)
-    k_pipe(CommDev c, void* buf, unsigned long long n, float scale, int K, unsigned long long cell) {
+    k_pipe(CommDev c, Src src, void* buf, unsigned long long n, float scale, int K, unsigned long long cell) {
   using namespace dev;
   using namespace pl;
   constexpr int WVB = Wire<MODE>::kBytes;
   constexpr int U = Unroll<W>::kU;
+  __shared__ uint32_t mail[2];  // [0]: chunks role A has finished, [1]: chunks role B has finished
   const uint32_t seq0 = op_begin(c);
   const uint32_t seq = seq0 * 4u + 1u;
   const unsigned long long stage = (seq0 & 1u) ? c.stage_off[1] : c.stage_off[0];
@@ -82,31 +113,35 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;  // P2P only
   uint8_t* const mine = c.peer[0];
   const int tid = threadIdx.x;
+  // chunks this CTA really has: cell (k, b) starts at (k*g + b)*cell, empty from the first k with start >= Ls on
+  int nk = 0;
+  while (nk < K && (static_cast<unsigned long long>(nk) * g + b) * cell < Ls) ++nk;
+  if (tid < 2) mail[tid] = 0;
+  __syncthreads();
 
-  if (tid < kA) {
-    // ================= role A: cast (NVLS) / scatter (P2P) =================
-    const int t = tid;
+  if (tid < kAS) {
+    // ================= role A data: cast (NVLS) / scatter (P2P) =================
+    const int t = tid - kA0;
     if (t == 0) trace_stamp(c, 0);
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < nk; ++k) {
       const unsigned long long lo = (static_cast<unsigned long long>(k) * g + b) * cell;
-      if (lo >= Ls) break;
       const unsigned long long hi = lo + cell < Ls ? lo + cell : Ls;
-      for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kA) * U) {
+      for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kAD) * U) {
         F8 x[U][W];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kA;
+          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kAD;
 #pragma unroll
           for (int jj = 0; jj < W; ++jj) {
             int j = c.rank + jj;
             if (j >= W) j -= W;
             const unsigned long long gv = j * Ls + v;
-            if (v < hi && gv < V) x[u][jj] = load_in<MODE>(buf, gv * 8, n, aligned);
+            if (v < hi && gv < V) x[u][jj] = load_src<MODE>(src, buf, gv * 8, n, aligned);
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kA;
+          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kAD;
 #pragma unroll
           for (int jj = 0; jj < W; ++jj) {
             int j = c.rank + jj;
@@ -122,41 +157,42 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
-      group_signal(c, 1, kA, t, 0, k, seq);
+      chunk_done(1, kAD, t, &mail[0], k);
     }
     if (t == 0) trace_stamp(c, 1);
-  } else if (tid < kA + kB) {
-    // ================= role B: move (NVLS) / reduce (P2P) =================
-    const int t = tid - kA;
+  } else if (tid < kB0) {
+    signaller(c, tid - kAS, &mail[0], 0, nk, seq);  // role A's signaller: X1[k]
+  } else if (tid < kBS) {
+    // ================= role B data: move (NVLS) / reduce (P2P) =================
+    const int t = tid - kB0;
     const unsigned long long base = c.rank * Ls;  // my slice
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < nk; ++k) {
       const unsigned long long lo = (static_cast<unsigned long long>(k) * g + b) * cell;
-      if (lo >= Ls) break;
       const unsigned long long hi = lo + cell < Ls ? lo + cell : Ls;
-      group_wait(c, 2, kB, t, 0, k, seq);
+      group_wait(c, 2, kBD, t, 0, k, seq);
       if (t == 0 && k == 0) trace_stamp(c, 2);
       if constexpr (ALG == kNvls) {
         constexpr int UM = MODE == B2_F32 ? 4 : 8;  // 128 B of switch-side reductions in flight per thread
         uint8_t* const mcs = c.mc + stage;
-        for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kB) * UM) {
+        for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kBD) * UM) {
           Wire<MODE> q[UM];
 #pragma unroll
           for (int u = 0; u < UM; ++u) {
-            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kB;
+            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
             if (v < hi && base + v < V) q[u] = mm_ld_reduce_wire<MODE>(mcs + (base + v) * WVB);
           }
 #pragma unroll
           for (int u = 0; u < UM; ++u) {
-            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kB;
+            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
             if (v < hi && base + v < V) mm_st_wire<MODE>(mcs + (base + v) * WVB, q[u]);
           }
         }
       } else {
-        for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kB) * U) {
+        for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kBD) * U) {
           Wire<MODE> w[U][W];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kB;
+            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
             if (v < hi && base + v < V) {
 #pragma unroll
               for (int r = 0; r < W; ++r) w[u][r] = ld_wire<MODE>(mine + stage + r * c.slice_cap + v * WVB);
@@ -164,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kB;
+            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
             if (v < hi && base + v < V) {
               F8 s = widen<MODE>(w[u][0]);
 #pragma unroll
@@ -174,23 +210,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
-      group_signal(c, 2, kB, t, 1, k, seq);
+      chunk_done(2, kBD, t, &mail[1], k);
     }
     if (t == 0) trace_stamp(c, 3);
+  } else if (tid < kC0) {
+    signaller(c, tid - kBS, &mail[1], 1, nk, seq);  // role B's signaller: X2[k]
   } else {
     // ================= role C: widen (NVLS) / gather (P2P) =================
-    const int t = tid - kA - kB;
-    for (int k = 0; k < K; ++k) {
+    const int t = tid - kC0;
+    for (int k = 0; k < nk; ++k) {
       const unsigned long long lo = (static_cast<unsigned long long>(k) * g + b) * cell;
-      if (lo >= Ls) break;
       const unsigned long long hi = lo + cell < Ls ? lo + cell : Ls;
-      group_wait(c, 3, kC, t, 1, k, seq);
+      group_wait(c, 3, kCD, t, 1, k, seq);
       if (t == 0 && k == 0) trace_stamp(c, 4);
-      for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kC) * U) {
+      for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kCD) * U) {
         Wire<MODE> w[U][W];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kC;
+          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kCD;
 #pragma unroll
           for (int jj = 0; jj < W; ++jj) {
             int j = c.rank + jj;
@@ -206,7 +243,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kC;
+          const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kCD;
 #pragma unroll
           for (int jj = 0; jj < W; ++jj) {
             int j = c.rank + jj;

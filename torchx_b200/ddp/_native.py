@@ -69,8 +69,10 @@ SYMBOLS = [
     "b2_comm_set_param",
     "b2_comm_status",
     "b2_comm_launch_count",
+    "b2_comm_last_algo",
     "b2_comm_trace",
     "b2_allreduce",
+    "b2_allreduce_gather",
     "b2_broadcast",
     "b2_barrier",
     "b2_local_pass",
@@ -124,7 +126,7 @@ def lib() -> ctypes.CDLL:
     L.b2_comm_create_local.argtypes = [ctypes.POINTER(vp), i, ctypes.POINTER(i), sz]
     L.b2_comm_destroy.restype = i
     L.b2_comm_destroy.argtypes = [vp]
-    for name in ("b2_comm_rank", "b2_comm_world", "b2_comm_device", "b2_comm_status", "b2_comm_caps"):
+    for name in ("b2_comm_rank", "b2_comm_world", "b2_comm_device", "b2_comm_status", "b2_comm_caps", "b2_comm_last_algo"):
         getattr(L, name).restype = i
         getattr(L, name).argtypes = [vp]
     L.b2_comm_set_timeout_ms.restype = i
@@ -139,6 +141,8 @@ def lib() -> ctypes.CDLL:
     L.b2_comm_trace.argtypes = [vp, i, ctypes.POINTER(u64), i]
     L.b2_allreduce.restype = i
     L.b2_allreduce.argtypes = [vp, vp, sz, i, f, i, vp]
+    L.b2_allreduce_gather.restype = i
+    L.b2_allreduce_gather.argtypes = [vp, vp, sz, vp, i, vp, i, f, i, vp]
     L.b2_broadcast.restype = i
     L.b2_broadcast.argtypes = [vp, vp, sz, i, vp]
     L.b2_barrier.restype = i

@@ -2,13 +2,15 @@
 
 Public surface mirrors ``torch.nn.parallel.DistributedDataParallel`` where the reference path relies on it
 (torch/nn/parallel/distributed.py:664-890: rank-0 parameter/buffer broadcast at construction, 25 MiB buckets with
-a 1 MiB first bucket, per-forward buffer broadcast, ``no_sync``), so a ``dist.ddp``-launched training script
-swaps one constructor.  Differences that matter for speed:
+a 1 MiB first bucket, per-forward buffer broadcast, ``no_sync``, ``module.``-prefixed state dict), so a
+``dist.ddp``-launched training script swaps one constructor.  Differences that matter for speed:
 
-  * each bucket is reduced by ONE fused kernel (fp32->bf16 cast + 1/W scale + NVSwitch P2P reduction + bf16->fp32)
+  * each bucket is reduced by ONE fused kernel (fp32->bf16 cast + 1/W scale + NVSwitch reduction + bf16->fp32)
     on a side stream while backward continues, instead of bf16_compress_hook's 4 launches;
-  * gradients land in persistent flat fp32 buckets and ``param.grad`` aliases them afterwards
-    (gradient_as_bucket_view semantics) - one multi-tensor copy per bucket, no per-parameter copy-out;
+  * zero-copy bucket fill: the kernel reads the gradients straight from the per-parameter tensors autograd produced
+    (a device pointer table per bucket) and writes the averaged values into the persistent flat bucket, which
+    ``param.grad`` aliases afterwards (gradient_as_bucket_view semantics) - the Reducer's copy-in pass
+    (reducer.cpp mark_variable_ready_dense) and its 8 bytes per element are gone;
   * the layout is the steady-state one from iteration 0 (no rebuild pass).
 """
 from __future__ import annotations
@@ -16,11 +18,14 @@ from __future__ import annotations
 import contextlib
 from typing import Dict, Iterator, List, Optional
 
+import numpy as np
 import torch
 from torch import nn
 
 from .bucketing import MIB, BucketSpec, plan_buckets
 from .comm import Communicator
+
+_SEG_RING = 4  # pinned pointer-table slots per bucket: the host may run this many iterations ahead of the GPU
 
 
 def _dense_non_overlapping(t: torch.Tensor) -> bool:
@@ -46,12 +51,30 @@ class _Bucket:
         self.params = params
         self.flat = torch.zeros(spec.numel, dtype=params[0].dtype, device=device)
         # like the Reducer, give each view the parameter's own (dense) strides so a channels_last weight gets a
-        # channels_last gradient view and the copy-in is a plain memcpy
+        # channels_last gradient view and the bucket's element order is the gradient's memory order
         self.views = [_view_like(self.flat[o : o + n], p) for o, n, p in zip(spec.offsets, spec.numels, params)]
+        # strides of the dims that matter (size > 1): two tensors with these equal have the same memory order
+        self.view_strides = [tuple(st for st, sz in zip(v.stride(), v.shape) if sz != 1) for v in self.views]
         self.pending = len(params)
         self.ready = False
         self.launched = False
         self.done = torch.cuda.Event()
+        # ---- zero-copy fill: device pointer table, refreshed per iteration (autograd hands out new tensors) ----
+        P = len(params)
+        begins = np.asarray(spec.offsets, dtype=np.int64)
+        ends = begins + np.asarray(spec.numels, dtype=np.int64)
+        nblk = (spec.numel + 4095) // 4096
+        blk = np.searchsorted(ends, np.arange(nblk, dtype=np.int64) * 4096, side="right").astype(np.int32)
+        self.block_index = torch.from_numpy(blk).to(device)
+        self.seg_host = [torch.empty((P, 3), dtype=torch.int64).pin_memory() for _ in range(_SEG_RING)]
+        self.seg_np = [h.numpy() for h in self.seg_host]
+        for a in self.seg_np:
+            a[:, 1] = begins
+            a[:, 2] = ends
+        self.seg_dev = torch.empty((P, 3), dtype=torch.int64, device=device)
+        self.seg_copied = [torch.cuda.Event() for _ in range(_SEG_RING)]
+        self.seg_used = [False] * _SEG_RING
+        self.seg_slot = 0
 
 
 class DistributedDataParallel(nn.Module):
@@ -64,13 +87,20 @@ class DistributedDataParallel(nn.Module):
         wire: str = "bf16",
         broadcast_buffers: bool = True,
         algo: str = "auto",
+        zero_copy: bool = True,
     ) -> None:
         super().__init__()
         self.module = module
-        self.comm = comm if comm is not None else Communicator.from_env()
+        if comm is None:
+            # one communicator per process: reuse the one init_pg("b200") created (each one owns a 1 GiB arena)
+            from torchx_b200 import distributed as _dist
+
+            comm = _dist._COMM if _dist._COMM is not None else Communicator.from_env()
+        self.comm = comm
         self.world_size = self.comm.world
         self.wire = wire
         self.algo = algo
+        self.zero_copy = zero_copy
         self.broadcast_buffers = broadcast_buffers
         self.require_backward_grad_sync = True
         self.device = torch.device("cuda", self.comm.device)
@@ -97,6 +127,8 @@ class DistributedDataParallel(nn.Module):
         self._next_bucket = 0
         self._callback_queued = False
         self._profile: Optional[list] = None
+        self.copied_in_buckets = 0   # buckets that needed the multi-tensor copy-in (zero-copy not applicable), for tests / bench
+        self.gathered_buckets = 0    # buckets whose gradients were read in place by the kernel
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad_ready) for p in self._params]
         self._sync_module_states()
 
@@ -136,8 +168,19 @@ class DistributedDataParallel(nn.Module):
                 self._broadcast_coalesced(bufs)
 
     # ---- training step -----------------------------------------------------------------------------
+    def _reset_reducer_state(self) -> None:
+        """What Reducer::prepare_for_backward does: a backward that raised midway (caught OOM, skipped batch) must
+        not leave stale counters behind - the engine drops its queued callbacks in that case."""
+        self._callback_queued = False
+        self._next_bucket = 0
+        for b in self.buckets:
+            b.pending, b.ready, b.launched = len(b.params), False, False
+
     def forward(self, *args, **kwargs):
         if torch.is_grad_enabled() and self.require_backward_grad_sync:
+            # a kernel that gave up on a stalled peer leaves undefined bucket contents: never train on them
+            self.comm.check()
+            self._reset_reducer_state()
             self._sync_buffers()
         return self.module(*args, **kwargs)
 
@@ -165,24 +208,56 @@ class DistributedDataParallel(nn.Module):
                 self._launch(self.buckets[self._next_bucket])
                 self._next_bucket += 1
 
+    def _gatherable(self, b: _Bucket, grads: List[torch.Tensor]) -> bool:
+        """The kernel can read a gradient in place when its memory order IS the bucket's element order: same dtype,
+        same (dense) strides as the bucket view the parameter's layout produced."""
+        dt = b.flat.dtype
+        for g, st in zip(grads, b.view_strides):
+            if g.dtype != dt or not g.is_cuda or tuple(s_ for s_, z in zip(g.stride(), g.shape) if z != 1) != st:
+                return False
+        return True
+
     def _launch(self, b: _Bucket) -> None:
-        src, dst = [], []
-        for p, v in zip(b.params, b.views):
+        grads = []
+        for p in b.params:
             g = p.grad
             if g is None:
                 raise RuntimeError("a parameter finished backward without a gradient (unused parameters are not supported)")
-            if g.data_ptr() != v.data_ptr():
-                src.append(g)
-                dst.append(v)
-        if src:
-            torch._foreach_copy_(dst, src)
+            grads.append(g)
+        gather = self.zero_copy and self._gatherable(b, grads)
+        if not gather:
+            src, dst = [], []
+            for g, v in zip(grads, b.views):
+                if g.data_ptr() != v.data_ptr():
+                    src.append(g)
+                    dst.append(v)
+            if src:
+                torch._foreach_copy_(dst, src)
+            self.copied_in_buckets += 1
+        else:
+            k = b.seg_slot
+            b.seg_slot = (k + 1) % _SEG_RING
+            if b.seg_used[k]:
+                b.seg_copied[k].synchronize()  # the H2D copy that last read this pinned slot (iterations ago) has executed
+            b.seg_np[k][:, 0] = [g.data_ptr() for g in grads]
+            self.gathered_buckets += 1
         cur = torch.cuda.current_stream(self.device)
         self._ready_event.record(cur)
         self._comm_stream.wait_event(self._ready_event)
         if self._profile is not None:
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record(self._comm_stream)
-        self.comm.allreduce_(b.flat, scale=1.0 / self.world_size, wire=self.wire, algo=self.algo, stream=self._comm_stream)
+        if gather:
+            with torch.cuda.stream(self._comm_stream):
+                b.seg_dev.copy_(b.seg_host[k], non_blocking=True)
+                b.seg_copied[k].record(self._comm_stream)
+                b.seg_used[k] = True
+            # the gradient tensors stay referenced by p.grad until _finalize_backward has made the compute stream wait for
+            # b.done, so the caching allocator cannot hand their memory out before the kernel has read it
+            self.comm.allreduce_gather_(b.flat, b.seg_dev, b.block_index, scale=1.0 / self.world_size, wire=self.wire, algo=self.algo,
+                                        stream=self._comm_stream)
+        else:
+            self.comm.allreduce_(b.flat, scale=1.0 / self.world_size, wire=self.wire, algo=self.algo, stream=self._comm_stream)
         b.done.record(self._comm_stream)
         if self._profile is not None:
             t1 = torch.cuda.Event(enable_timing=True)
@@ -203,6 +278,7 @@ class DistributedDataParallel(nn.Module):
                 cur.wait_event(b.done)
                 for p, v in zip(b.params, b.views):
                     p.grad = v  # gradient_as_bucket_view: the optimizer reads the averaged bucket in place
+            self.comm.check()
         finally:
             self._next_bucket = 0
             for b in self.buckets:
@@ -213,20 +289,20 @@ class DistributedDataParallel(nn.Module):
         self._profile = []
 
     def stop_profile(self) -> dict:
-        """Sum of device time and algorithmic bytes (read the bucket once + write it once) over the bucket
-        kernels launched since start_profile()."""
+        """Sum of device time and algorithmic bytes (read the gradients once + write the bucket once) over the bucket
+        kernels launched since start_profile(), plus the per-bucket-index mean device time."""
         torch.cuda.synchronize(self.device)
         prof, self._profile = self._profile or [], None
-        seconds = sum(a.elapsed_time(b) for a, b, _ in prof) * 1e-3
-        name = "k_local_pass (W=1 fused cast/scale pass)" if self.world_size == 1 else "k_oneshot/k_twoshot (fused bucket allreduce)"
-        return {"name": name, "launches": len(prof), "seconds": seconds, "alg_bytes": sum(n for _, _, n in prof)}
-
-    # ---- conveniences mirroring nn.parallel.DistributedDataParallel ------------------------------------
-    def state_dict(self, *args, **kwargs):
-        return self.module.state_dict(*args, **kwargs)
-
-    def load_state_dict(self, *args, **kwargs):
-        return self.module.load_state_dict(*args, **kwargs)
+        times = [a.elapsed_time(b) * 1e-3 for a, b, _ in prof]
+        seconds = sum(times)
+        nb = len(self.buckets)
+        per_bucket = []
+        if prof and len(prof) % nb == 0:
+            for i in range(nb):
+                ts = times[i::nb]
+                per_bucket.append(round(sum(ts) / len(ts) * 1e6, 2))
+        name = "k_local_pass (W=1 fused cast/scale pass)" if self.world_size == 1 else "k_pipe / k_oneshot / k_twoshot (fused bucket allreduce)"
+        return {"name": name, "launches": len(prof), "seconds": seconds, "alg_bytes": sum(n for _, _, n in prof), "per_bucket_us": per_bucket}
 
     def bucket_sizes_mib(self) -> List[float]:
         return [round(b.spec.nbytes / MIB, 2) for b in self.buckets]

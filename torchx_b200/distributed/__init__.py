@@ -110,6 +110,7 @@ def barrier() -> None:
     if _COMM is not None and not dist.is_initialized():
         _COMM.barrier()
         torch.cuda.current_stream(_COMM.device).synchronize()
+        _COMM.check()  # a barrier kernel that gave up on a stalled peer must not let this rank into the critical section
     elif dist.is_initialized():
         dist.barrier()
 
