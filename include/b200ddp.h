@@ -169,19 +169,20 @@ int b2_allreduce(b2_comm_t* comm, void* buf, size_t n_elems, int mode, float sca
  * bucket_view.copy_(grad); with gradient_as_bucket_view the copy still happens whenever autograd produced the gradient
  * elsewhere, torch/nn/parallel/distributed.py:589-600) - 8 bytes per element and one multi-tensor launch per bucket.
  *      out[i] <- round( sum_r wire( scale * segment_r(i)[i - begin] ) ),   i in [0, n_elems)
- * `segments_dev`: DEVICE array, in bucket order and without gaps: segment k covers bucket elements [begin, end) and reads
- * them from `src` (this rank's tensor of the bucket's dtype; dense in the bucket's element order).
- * `block_index_dev`: DEVICE array of ceil(n_elems / 4096) entries: index of the segment containing element 4096 * j.
- * Both arrays must stay valid until the launch has executed.  `out` is this rank's bucket.
+ * `segments`: HOST array of 1..B2_MAX_SEGMENTS entries in bucket order and without gaps: segment k covers bucket elements
+ * [begin, end) and reads them from the DEVICE pointer `src` (this rank's tensor of the bucket's dtype, dense in the
+ * bucket's element order; it may alias `out`).  The table is copied into the kernel parameters by this call: it need not
+ * outlive it.  `out` is this rank's bucket.  More parameters than B2_MAX_SEGMENTS: B2_EINVAL (copy in, then b2_allreduce).
  */
+#define B2_MAX_SEGMENTS 128
 typedef struct b2_segment {
   const void* src;
   uint64_t begin;
   uint64_t end;
 } b2_segment_t;
 
-int b2_allreduce_gather(b2_comm_t* comm, void* out, size_t n_elems, const b2_segment_t* segments_dev, int n_segments,
-                        const uint32_t* block_index_dev, int mode, float scale, int algo, void* stream);
+int b2_allreduce_gather(b2_comm_t* comm, void* out, size_t n_elems, const b2_segment_t* segments, int n_segments,
+                        int mode, float scale, int algo, void* stream);
 
 /* Broadcast `bytes` bytes at `buf` from rank `root` to every rank (bit-exact copy). */
 int b2_broadcast(b2_comm_t* comm, void* buf, size_t bytes, int root, void* stream);

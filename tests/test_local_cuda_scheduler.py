@@ -222,3 +222,51 @@ def test_two_nodes_of_two_workers_on_one_box_gloo(tmp_path):
         assert ranks == [0, 1, 2, 3]
         assert all("same_on_all_ranks=True" in ln for lines in per_node for ln in lines if "sha256" in ln)
         assert any(ln.startswith("[2]:") or ln.startswith("[3]:") for ln in per_node[1])  # node 1 hosts global ranks 2, 3
+
+
+def test_gang_supervision_timeout_and_sentinel_files(sched, tmp_path):
+    """process_monitor semantics for the whole gang (reference torchx/apps/utils/process_monitor.py:65-118): a job_timeout
+    terminates every worker and fails the app; exit_on_file does the same on demand; start_on_file holds the launch."""
+    out = tmp_path / "out"
+    out.mkdir()
+    with mock.patch.object(sched, "_cuda_device_count", return_value=0):
+        t0 = time.time()
+        app_id = sched.submit(ddp(str(out), "sleep", script=WORKER, j="1x2"), {"log_dir": str(tmp_path / "l1"), "job_timeout": 1.0})
+        time.sleep(0.3)
+        pids = [r.proc.pid for r in sched._apps[app_id].replicas()]
+        d = _wait(sched, app_id)
+        assert d.state == AppState.FAILED and "job timeout" in d.msg and time.time() - t0 < 30
+        assert sched._apps[app_id].exit_code == 34
+        for pid in pids:
+            with pytest.raises(ProcessLookupError):
+                os.kill(pid, 0)
+        stop = tmp_path / "stop"
+        app_id = sched.submit(ddp(str(out), "sleep", script=WORKER, j="1x2"), {"log_dir": str(tmp_path / "l2"), "exit_on_file": str(stop)})
+        time.sleep(0.5)
+        assert sched.describe(app_id).state == AppState.RUNNING
+        stop.write_text("now")
+        d = _wait(sched, app_id)
+        assert d.state == AppState.FAILED and str(stop) in d.msg
+        go = tmp_path / "go"
+        app_id = sched.submit(ddp(str(out), "ok", script=WORKER, j="1x2"), {"log_dir": str(tmp_path / "l3"), "start_on_file": str(go)})
+        time.sleep(0.5)
+        assert sched.describe(app_id).state == AppState.PENDING and not sched._apps[app_id].replicas()
+        go.write_text("go")
+        assert _wait(sched, app_id).state == AppState.SUCCEEDED
+        app_id = sched.submit(ddp(str(out), "ok", script=WORKER, j="1x2"),
+                              {"log_dir": str(tmp_path / "l4"), "start_on_file": str(tmp_path / "never"), "job_timeout": 0.5})
+        d = _wait(sched, app_id)
+        assert d.state == AppState.FAILED and "before launching" in d.msg
+
+
+def test_process_monitor_module(tmp_path):
+    from torchx_b200.apps.utils import process_monitor as pm
+
+    assert pm.supervise(sys.executable, ["-c", "import sys; sys.exit(7)"], poll_rate=0.1) == 7
+    t0 = time.time()
+    rc = pm.supervise(sys.executable, ["-c", "import time; time.sleep(60)"], timeout=0.5, poll_rate=0.1, kill_timeout=5)
+    assert rc != 0 and time.time() - t0 < 20
+    assert pm.supervise(sys.executable, ["-c", "pass"], timeout=0.3, start_on_file=str(tmp_path / "nope"), poll_rate=0.1) == pm.TIMEOUT_EXIT_CODE
+    stop = tmp_path / "stop"
+    stop.write_text("x")
+    assert pm.supervise(sys.executable, ["-c", "import time; time.sleep(60)"], exit_on_file=str(stop), poll_rate=0.1, kill_timeout=5) != 0

@@ -75,9 +75,12 @@ def main():
     ap.add_argument("--per-class", type=int, default=8192)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--out", default="gpurun_out/nvls_probe.npz")
+    ap.add_argument("--stage-mb", type=int, default=8)
     a = ap.parse_args()
+    if "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_multiprocess(a)
     W = a.world or torch.cuda.device_count()
-    comms = Communicator.create_local(list(range(W)), stage_mb=8)
+    comms = Communicator.create_local(list(range(W)), stage_mb=a.stage_mb)
     print(f"world={W} caps={comms[0].caps} multicast={comms[0].has_multicast}", flush=True)
     if not comms[0].has_multicast:
         print("NO MULTICAST on this box: nothing to probe")
@@ -99,6 +102,26 @@ def main():
             c.check()
         for r in range(W):
             outs[rep, r] = tens[r].view(torch.int16).cpu().numpy().view(np.uint16)
+    # the same bf16 values held in fp32 buckets (mode F32_WIRE_BF16, scale 1): the DDP path's own configuration
+    outs_fw = np.zeros((a.reps, W, n), dtype=np.uint16)
+    as_f32 = (bits.astype(np.uint32) << 16).view(np.float32)
+    for rep in range(a.reps):
+        tens = [torch.from_numpy(as_f32[r].copy()).to(f"cuda:{r}") for r in range(W)]
+        for r, (c, s) in enumerate(zip(comms, streams)):
+            c.allreduce_(tens[r], scale=1.0, wire="bf16", algo="nvls", stream=s)
+        for s in streams:
+            s.synchronize()
+        for r in range(W):
+            outs_fw[rep, r] = (tens[r].cpu().numpy().view(np.uint32) >> 16).astype(np.uint16)
+    # ... and through the rank-order P2P kernel, as the on-device reference for the same inputs
+    outs_p2p = np.zeros((W, n), dtype=np.uint16)
+    tens = [torch.from_numpy(bits[r].view(np.int16).copy()).to(f"cuda:{r}").view(torch.bfloat16) for r in range(W)]
+    for r, (c, s) in enumerate(zip(comms, streams)):
+        c.allreduce_(tens[r], scale=1.0, wire="bf16", algo="twoshot", stream=s)
+    for s in streams:
+        s.synchronize()
+    for r in range(W):
+        outs_p2p[r] = tens[r].view(torch.int16).cpu().numpy().view(np.uint16)
     # fp32-wire NVLS (multimem.ld_reduce.add.f32): wide-spread fp32 inputs
     rng = np.random.default_rng(1)
     f_in = (rng.standard_normal((W, a.per_class)) * np.exp2(rng.integers(-20, 21, (W, a.per_class)))).astype(np.float32)
@@ -112,15 +135,50 @@ def main():
         for r in range(W):
             f_out[rep, r] = tens[r].cpu().numpy()
     os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
-    np.savez_compressed(a.out, multicast=np.array([1]), world=np.array([W]), bf16_in=bits, bf16_out=outs, f32_in=f_in, f32_out=f_out,
+    np.savez_compressed(a.out, multicast=np.array([1]), world=np.array([W]), bf16_in=bits, bf16_out=outs, bf16_out_f32wire=outs_fw, bf16_out_p2p=outs_p2p,
+                        f32_in=f_in, f32_out=f_out,
                         class_names=np.array([nm for nm, _, _ in names]), class_start=np.array([s for _, s, _ in names]),
                         class_len=np.array([ln for _, _, ln in names]))
     same_reps = bool(np.all(outs == outs[0]))
     same_ranks = bool(np.all(outs[:, 1:] == outs[:, :1]))
+    print(f"nvls(bf16 bucket) == p2p rank-order: {int((outs[0, 0] != outs_p2p[0]).sum())} of {n} differ; nvls(f32 bucket, bf16 wire) vs p2p: "
+          f"{int((outs_fw[0, 0] != outs_p2p[0]).sum())} differ", flush=True)
     print(f"saved {a.out}: n={n}; identical across reps: {same_reps}; identical across ranks: {same_ranks}; "
           f"f32 identical across reps: {bool(np.array_equal(f_out[0], f_out[-1], equal_nan=True))}", flush=True)
     for c in comms:
         c.close()
+
+
+def main_multiprocess(a):
+    """Under torchrun: one process per GPU (the production topology); rank r feeds row r of the same crafted inputs."""
+    rank, W = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    comm = Communicator.from_env(stage_mb=a.stage_mb)
+    comm.set_timeout(30.0)
+    bits, names = craft(W, a.per_class)
+    n = bits.shape[1]
+    res = {}
+    for tag, algo in (("nvls", "nvls"), ("p2p", "twoshot")):
+        if algo == "nvls" and not comm.has_multicast:
+            continue
+        t = torch.from_numpy(bits[rank].view(np.int16).copy()).cuda().view(torch.bfloat16)
+        comm.allreduce_(t, scale=1.0, wire="bf16", algo=algo)
+        torch.cuda.synchronize()
+        res[f"bf16_out_{tag}"] = t.view(torch.int16).cpu().numpy().view(np.uint16)
+        f = torch.from_numpy((bits[rank].astype(np.uint32) << 16).view(np.float32).copy()).cuda()
+        comm.allreduce_(f, scale=1.0, wire="bf16", algo=algo)
+        torch.cuda.synchronize()
+        res[f"f32wire_out_{tag}"] = (f.cpu().numpy().view(np.uint32) >> 16).astype(np.uint16)
+    comm.check()
+    if rank == 0:
+        np.savez_compressed(a.out, world=np.array([W]), bf16_in=bits, class_names=np.array([nm for nm, _, _ in names]),
+                            class_start=np.array([s for _, s, _ in names]), class_len=np.array([ln for _, _, ln in names]), **res)
+        if "bf16_out_nvls" in res:
+            print(f"multi-process W={W}: nvls(bf16) vs p2p differ in {int((res['bf16_out_nvls'] != res['bf16_out_p2p']).sum())} of {n}; "
+                  f"nvls(f32 bucket) vs p2p differ in {int((res['f32wire_out_nvls'] != res['f32wire_out_p2p']).sum())}", flush=True)
+    comm.barrier()
+    torch.cuda.synchronize()
+    comm.close()
 
 
 if __name__ == "__main__":

@@ -366,7 +366,7 @@ cudaError_t launch_local(const Src& src, void* buf, unsigned long long n, float 
   static const bool use_tma = env_size("B2_LOCAL_TMA", 1) != 0;
   static const unsigned long long tma_min = env_size("B2_LOCAL_TMA_MIN_MB", 256) << 20;
   const unsigned long long nbytes = n * (MODE == B2_BF16 ? 2 : 4);
-  if (use_tma && src.segs == nullptr && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20) && nbytes >= tma_min) {
+  if (use_tma && src.nseg == 0 && (reinterpret_cast<uintptr_t>(buf) & 15u) == 0 && nbytes >= (1ull << 20) && nbytes >= tma_min) {
     const unsigned long long ntiles = nbytes / tma::kTileBytes;
     unsigned long long g = ntiles < 148ull * 2 ? ntiles : 148ull * 2;  // persistent: 2 CTAs (2 x 64 KiB rings) per SM
     constexpr int kSmem = tma::kStages * tma::kTileBytes;
@@ -400,6 +400,8 @@ cudaError_t launch_mode(const CommDev& d, const Src& src, int mode, int kind, in
       return launch_by_world<B2_BF16>(d, src, kind, grid, p, buf, n, scale, s);
   }
 }
+
+const Src kNoSrc = {};  // nseg == 0: the collective reads the bucket itself
 
 int local_pass_impl(const Src& src, void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
   if (n_elems == 0) return B2_OK;
@@ -935,10 +937,10 @@ int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
 }
 
 int b2_local_pass(void* buf, size_t n_elems, int mode, float scale, int device, void* stream) {
-  return local_pass_impl(Src{nullptr, nullptr, 0}, buf, n_elems, mode, scale, device, stream);
+  return local_pass_impl(kNoSrc, buf, n_elems, mode, scale, device, stream);
 }
 
-static int allreduce_impl(b2_comm_t* c, Src src, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
+static int allreduce_impl(b2_comm_t* c, Src& src, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
   if (!c) return fail(B2_EINVAL, "null communicator");
   if (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16)
     return fail(B2_EINVAL, "unknown mode %d", mode);
@@ -951,7 +953,7 @@ static int allreduce_impl(b2_comm_t* c, Src src, void* buf, size_t n_elems, int 
     return fail(B2_ESTATE, "communicator poisoned by an earlier peer-wait timeout");
   const int W = c->d.world;
   if (W == 1) {
-    if (mode == B2_F32 && scale == 1.0f && src.segs == nullptr) return B2_OK;  // identity
+    if (mode == B2_F32 && scale == 1.0f && src.nseg == 0) return B2_OK;  // identity
     int rc = local_pass_impl(src, buf, n_elems, mode, scale, c->device, stream);
     if (rc == B2_OK) c->launches++;
     return rc;
@@ -1001,16 +1003,30 @@ static int allreduce_impl(b2_comm_t* c, Src src, void* buf, size_t n_elems, int 
 }
 
 int b2_allreduce(b2_comm_t* c, void* buf, size_t n_elems, int mode, float scale, int algo, void* stream) {
-  return allreduce_impl(c, Src{nullptr, nullptr, 0}, buf, n_elems, mode, scale, algo, stream);
+  Src src = kNoSrc;
+  return allreduce_impl(c, src, buf, n_elems, mode, scale, algo, stream);
 }
 
-int b2_allreduce_gather(b2_comm_t* c, void* out, size_t n_elems, const b2_segment_t* segments_dev, int n_segments,
-                        const uint32_t* block_index_dev, int mode, float scale, int algo, void* stream) {
-  if (n_elems > 0 && (!segments_dev || n_segments <= 0 || !block_index_dev))
-    return fail(B2_EINVAL, "b2_allreduce_gather: segment table / block index missing");
-  static_assert(sizeof(b2_segment_t) == sizeof(Seg), "ABI segment layout");
-  return allreduce_impl(c, Src{reinterpret_cast<const Seg*>(segments_dev), block_index_dev, 0}, out, n_elems, mode, scale,
-                        algo, stream);
+int b2_allreduce_gather(b2_comm_t* c, void* out, size_t n_elems, const b2_segment_t* segments, int n_segments, int mode,
+                        float scale, int algo, void* stream) {
+  if (n_elems == 0) return B2_OK;
+  if (!segments || n_segments <= 0 || n_segments > B2_MAX_SEGMENTS)
+    return fail(B2_EINVAL, "b2_allreduce_gather: need 1..%d segments (got %d)", B2_MAX_SEGMENTS, n_segments);
+  Src src;
+  src.nseg = n_segments;
+  src.off = 0;
+  unsigned long long at = 0;
+  for (int i = 0; i < n_segments; ++i) {
+    if (segments[i].begin != at || segments[i].end <= at || !segments[i].src)
+      return fail(B2_EINVAL, "b2_allreduce_gather: segment %d does not continue the bucket at element %llu", i, at);
+    src.ptr[i] = segments[i].src;
+    src.begin[i] = at;
+    at = segments[i].end;
+  }
+  if (at != n_elems) return fail(B2_EINVAL, "b2_allreduce_gather: segments cover %llu elements, bucket has %zu", at, n_elems);
+  for (int i = n_segments; i <= B2_MAX_SEGMENTS; ++i) src.begin[i] = at;
+  for (int i = n_segments; i < B2_MAX_SEGMENTS; ++i) src.ptr[i] = nullptr;
+  return allreduce_impl(c, src, out, n_elems, mode, scale, algo, stream);
 }
 
 int b2_broadcast(b2_comm_t* c, void* buf, size_t bytes, int root, void* stream) {

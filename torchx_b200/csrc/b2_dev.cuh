@@ -57,19 +57,18 @@ struct CommDev {
                                     // 8 slots per CTA (see include/b200ddp.h)
 };
 
-// Where a collective reads its INPUT from.  segs == nullptr: the bucket itself (in place).  Otherwise the bucket is only
-// the OUTPUT and the input is gathered straight from the per-parameter gradient tensors ("zero-copy bucket fill": the
-// Reducer's copy-in pass, torch/csrc/distributed/c10d/reducer.cpp mark_variable_ready_dense, disappears into the
-// first phase of the allreduce):  segs[i] = {device pointer, first bucket element, one-past-last bucket element} in
-// bucket order, covering [0, n) without gaps;  blk[e >> 12] = index of the segment holding bucket element (e & ~4095).
-struct Seg {
-  const void* src;
-  unsigned long long begin, end;
-};
+// Where a collective reads its INPUT from.  nseg == 0: the bucket itself (in place).  Otherwise the bucket is only the
+// OUTPUT and the input is gathered straight from the per-parameter gradient tensors ("zero-copy bucket fill": the
+// Reducer's copy-in pass, torch/csrc/distributed/c10d/reducer.cpp mark_variable_ready_dense, disappears into the first
+// phase of the allreduce): segment i holds bucket elements [begin[i], begin[i+1]) at ptr[i], in bucket order and without
+// gaps.  The table travels BY VALUE in the kernel parameters (constant bank: ~2 KiB of the 4 KiB limit) - no device-side
+// table, no host-to-device copy to order against the launch, nothing to keep alive.
+constexpr int kMaxSegs = B2_MAX_SEGMENTS;
 struct Src {
-  const Seg* segs;
-  const uint32_t* blk;
+  int nseg;
   unsigned long long off;  // bucket element index of this launch's element 0 (messages larger than a stage are cut up)
+  const void* ptr[kMaxSegs];
+  unsigned long long begin[kMaxSegs + 1];
 };
 
 }  // namespace
@@ -369,13 +368,18 @@ __device__ __forceinline__ bool buf_aligned(const void* buf) {
 template <int MODE>
 __device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned long long e, unsigned long long n,
                                        bool aligned) {
-  if (src.segs == nullptr) return load_in<MODE>(buf, e, n, aligned);
+  if (src.nseg == 0) return load_in<MODE>(buf, e, n, aligned);
   using Elem = typename std::conditional<MODE == B2_BF16, uint16_t, float>::type;
   const unsigned long long ge = e + src.off;  // bucket coordinates
-  uint32_t s = __ldg(src.blk + (ge >> 12));
-  while (ge >= __ldg(&src.segs[s].end)) ++s;
-  const Elem* base = static_cast<const Elem*>(src.segs[s].src);
-  const unsigned long long sb = __ldg(&src.segs[s].begin), se = __ldg(&src.segs[s].end);
+  int lo = 0, hi = src.nseg;                  // begin[lo] <= ge < begin[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (ge >= src.begin[mid]) lo = mid;
+    else hi = mid;
+  }
+  int s = lo;
+  unsigned long long sb = src.begin[s], se = src.begin[s + 1];
+  const Elem* base = static_cast<const Elem*>(src.ptr[s]);
   const Elem* p = base + (ge - sb);
   F8 x;
   if (e + 8 <= n && ge + 8 <= se && (reinterpret_cast<uintptr_t>(p) & (MODE == B2_BF16 ? 15u : 31u)) == 0) {
@@ -387,22 +391,21 @@ __device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned
       x = ldg_f8(p);
     }
   } else {  // the vec straddles parameters, is not 32 B-aligned in its tensor, or is the ragged tail
-    unsigned long long cur_b = sb, cur_e = se;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float v = 0.f;
       if (e + i < n) {
         const unsigned long long g = ge + i;
-        while (g >= cur_e) {
+        while (g >= se) {
           ++s;
-          base = static_cast<const Elem*>(src.segs[s].src);
-          cur_b = __ldg(&src.segs[s].begin);
-          cur_e = __ldg(&src.segs[s].end);
+          sb = se;
+          se = src.begin[s + 1];
+          base = static_cast<const Elem*>(src.ptr[s]);
         }
         if constexpr (MODE == B2_BF16)
-          v = __uint_as_float(static_cast<uint32_t>(base[g - cur_b]) << 16);
+          v = __uint_as_float(static_cast<uint32_t>(base[g - sb]) << 16);
         else
-          v = base[g - cur_b];
+          v = base[g - sb];
       }
       x.v[i] = v;
     }

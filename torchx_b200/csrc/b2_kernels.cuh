@@ -6,7 +6,7 @@
 
 // W == 1 (and the single-GPU roofline probe): x <- round(wire(scale * x)), one streaming pass.
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) k_local_pass(Src src, void* buf, unsigned long long n, float scale) {
+__global__ void __launch_bounds__(kThreads) k_local_pass(const __grid_constant__ Src src, void* buf, unsigned long long n, float scale) {
   using namespace dev;
   const bool aligned = buf_aligned<MODE>(buf);
   const unsigned long long V = (n + 7) / 8;
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(tma::kTmaThreads) k_local_pass_tma(void* buf, 
 // One-shot: latency regime.  Wire traffic per rank: (W-1) * S out, (W-1) * S in.
 template <int MODE, int W>
 __global__ void __launch_bounds__(kThreads, 1)
-    k_oneshot(CommDev c, Src src, void* buf, unsigned long long n, float scale) {
+    k_oneshot(CommDev c, const __grid_constant__ Src src, void* buf, unsigned long long n, float scale) {
   using namespace dev;
   constexpr int WVB = Wire<MODE>::kBytes;
   constexpr int U = Unroll<W>::kU;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 // synchronisation needed is among the CTAs with equal blockIdx.x across ranks (no grid sync).
 template <int MODE, int W>
 __global__ void __launch_bounds__(kThreads, 1)
-    k_twoshot(CommDev c, Src src, void* buf, unsigned long long n, float scale) {
+    k_twoshot(CommDev c, const __grid_constant__ Src src, void* buf, unsigned long long n, float scale) {
   using namespace dev;
   constexpr int WVB = Wire<MODE>::kBytes;
   constexpr int U = Unroll<W>::kU;

@@ -97,7 +97,7 @@ __device__ __forceinline__ void group_wait(const CommDev& c, int id, int count, 
 
 template <int MODE, int W, int ALG>
 __global__ void __launch_bounds__(kThreads, 1)
-    k_pipe(CommDev c, Src src, void* buf, unsigned long long n, float scale, int K, unsigned long long cell) {
+    k_pipe(CommDev c, const __grid_constant__ Src src, void* buf, unsigned long long n, float scale, int K, unsigned long long cell) {
   using namespace dev;
   using namespace pl;
   constexpr int WVB = Wire<MODE>::kBytes;

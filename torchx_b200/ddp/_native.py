@@ -79,6 +79,15 @@ SYMBOLS = [
 ]
 
 
+B2_MAX_SEGMENTS = 128
+
+
+class B2Segment(ctypes.Structure):
+    """b2_segment_t: bucket elements [begin, end) live at device pointer src."""
+
+    _fields_ = [("src", ctypes.c_void_p), ("begin", ctypes.c_uint64), ("end", ctypes.c_uint64)]
+
+
 class B2Error(RuntimeError):
     def __init__(self, code: int, msg: str) -> None:
         super().__init__(f"libb200ddp error {code}: {msg}")
@@ -142,7 +151,7 @@ def lib() -> ctypes.CDLL:
     L.b2_allreduce.restype = i
     L.b2_allreduce.argtypes = [vp, vp, sz, i, f, i, vp]
     L.b2_allreduce_gather.restype = i
-    L.b2_allreduce_gather.argtypes = [vp, vp, sz, vp, i, vp, i, f, i, vp]
+    L.b2_allreduce_gather.argtypes = [vp, vp, sz, ctypes.POINTER(B2Segment), i, i, f, i, vp]
     L.b2_broadcast.restype = i
     L.b2_broadcast.argtypes = [vp, vp, sz, i, vp]
     L.b2_barrier.restype = i

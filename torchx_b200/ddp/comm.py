@@ -159,20 +159,16 @@ class Communicator:
                                      ctypes.c_float(scale), ALGOS[algo], ctypes.c_void_p(_stream_ptr(stream, self.device))))
         return t
 
-    def allreduce_gather_(self, out: torch.Tensor, segments: torch.Tensor, block_index: torch.Tensor, scale: Optional[float] = None,
-                          wire: str = "bf16", algo: str = "auto", stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
+    def allreduce_gather_(self, out: torch.Tensor, segments, n_segments: int, scale: Optional[float] = None, wire: str = "bf16",
+                          algo: str = "auto", stream: Optional[torch.cuda.Stream] = None) -> torch.Tensor:
         """``out <- round(sum_r wire(scale * concat(segments_r)))``: the bucket is only written; the input is read
         straight from the tensors the segment table points at (include/b200ddp.h: b2_allreduce_gather).  ``segments`` is a
-        device int64 tensor [P, 3] of (data_ptr, begin, end) rows, ``block_index`` a device int32 tensor."""
+        ctypes array of ``_native.B2Segment`` (device pointer, begin, end) covering the bucket in order; it is copied into
+        the kernel parameters by the call."""
         self._check_tensor(out)
         if scale is None:
             scale = 1.0 / self.world
-        if segments.dtype != torch.int64 or segments.dim() != 2 or segments.shape[1] != 3 or not segments.is_contiguous():
-            raise ValueError("segments must be a contiguous int64 [P, 3] tensor")
-        if block_index.dtype != torch.int32 or block_index.numel() < (out.numel() + 4095) // 4096:
-            raise ValueError("block_index must be int32 with ceil(n / 4096) entries")
-        N.check(N.lib().b2_allreduce_gather(self._h, ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.c_void_p(segments.data_ptr()),
-                                            segments.shape[0], ctypes.c_void_p(block_index.data_ptr()), mode_for(out, wire),
+        N.check(N.lib().b2_allreduce_gather(self._h, ctypes.c_void_p(out.data_ptr()), out.numel(), segments, n_segments, mode_for(out, wire),
                                             ctypes.c_float(scale), ALGOS[algo], ctypes.c_void_p(_stream_ptr(stream, self.device))))
         return out
 

@@ -18,14 +18,12 @@ from __future__ import annotations
 import contextlib
 from typing import Dict, Iterator, List, Optional
 
-import numpy as np
 import torch
 from torch import nn
 
 from .bucketing import MIB, BucketSpec, plan_buckets
+from . import _native as N
 from .comm import Communicator
-
-_SEG_RING = 4  # pinned pointer-table slots per bucket: the host may run this many iterations ahead of the GPU
 
 
 def _dense_non_overlapping(t: torch.Tensor) -> bool:
@@ -59,22 +57,15 @@ class _Bucket:
         self.ready = False
         self.launched = False
         self.done = torch.cuda.Event()
-        # ---- zero-copy fill: device pointer table, refreshed per iteration (autograd hands out new tensors) ----
+        # ---- zero-copy fill: the segment table (begin / end fixed, pointers refreshed per iteration: autograd hands out
+        # new tensors); it travels in the kernel parameters, so nothing is copied to the device or has to stay alive
         P = len(params)
-        begins = np.asarray(spec.offsets, dtype=np.int64)
-        ends = begins + np.asarray(spec.numels, dtype=np.int64)
-        nblk = (spec.numel + 4095) // 4096
-        blk = np.searchsorted(ends, np.arange(nblk, dtype=np.int64) * 4096, side="right").astype(np.int32)
-        self.block_index = torch.from_numpy(blk).to(device)
-        self.seg_host = [torch.empty((P, 3), dtype=torch.int64).pin_memory() for _ in range(_SEG_RING)]
-        self.seg_np = [h.numpy() for h in self.seg_host]
-        for a in self.seg_np:
-            a[:, 1] = begins
-            a[:, 2] = ends
-        self.seg_dev = torch.empty((P, 3), dtype=torch.int64, device=device)
-        self.seg_copied = [torch.cuda.Event() for _ in range(_SEG_RING)]
-        self.seg_used = [False] * _SEG_RING
-        self.seg_slot = 0
+        self.segments = None
+        if P <= N.B2_MAX_SEGMENTS:
+            self.segments = (N.B2Segment * P)()
+            for i, (o, n) in enumerate(zip(spec.offsets, spec.numels)):
+                self.segments[i].begin = o
+                self.segments[i].end = o + n
 
 
 class DistributedDataParallel(nn.Module):
@@ -224,7 +215,7 @@ class DistributedDataParallel(nn.Module):
             if g is None:
                 raise RuntimeError("a parameter finished backward without a gradient (unused parameters are not supported)")
             grads.append(g)
-        gather = self.zero_copy and self._gatherable(b, grads)
+        gather = self.zero_copy and b.segments is not None and self._gatherable(b, grads)
         if not gather:
             src, dst = [], []
             for g, v in zip(grads, b.views):
@@ -235,11 +226,8 @@ class DistributedDataParallel(nn.Module):
                 torch._foreach_copy_(dst, src)
             self.copied_in_buckets += 1
         else:
-            k = b.seg_slot
-            b.seg_slot = (k + 1) % _SEG_RING
-            if b.seg_used[k]:
-                b.seg_copied[k].synchronize()  # the H2D copy that last read this pinned slot (iterations ago) has executed
-            b.seg_np[k][:, 0] = [g.data_ptr() for g in grads]
+            for seg, g in zip(b.segments, grads):
+                seg.src = g.data_ptr()
             self.gathered_buckets += 1
         cur = torch.cuda.current_stream(self.device)
         self._ready_event.record(cur)
@@ -248,13 +236,9 @@ class DistributedDataParallel(nn.Module):
             t0 = torch.cuda.Event(enable_timing=True)
             t0.record(self._comm_stream)
         if gather:
-            with torch.cuda.stream(self._comm_stream):
-                b.seg_dev.copy_(b.seg_host[k], non_blocking=True)
-                b.seg_copied[k].record(self._comm_stream)
-                b.seg_used[k] = True
             # the gradient tensors stay referenced by p.grad until _finalize_backward has made the compute stream wait for
             # b.done, so the caching allocator cannot hand their memory out before the kernel has read it
-            self.comm.allreduce_gather_(b.flat, b.seg_dev, b.block_index, scale=1.0 / self.world_size, wire=self.wire, algo=self.algo,
+            self.comm.allreduce_gather_(b.flat, b.segments, len(b.params), scale=1.0 / self.world_size, wire=self.wire, algo=self.algo,
                                         stream=self._comm_stream)
         else:
             self.comm.allreduce_(b.flat, scale=1.0 / self.world_size, wire=self.wire, algo=self.algo, stream=self._comm_stream)

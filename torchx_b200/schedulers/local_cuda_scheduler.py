@@ -89,6 +89,16 @@ class CudaOpts(Opts):
     master_port: int = 0
     """MASTER_PORT handed to the workers (0 = pick a free port at launch)."""
 
+    job_timeout: float = 0.0
+    """Seconds after which the whole gang is terminated (SIGTERM, then SIGKILL) and the app FAILED with exit code 34 -
+    what wrapping every replica in the reference's ``torchx.apps.utils.process_monitor --timeout`` does, for the gang."""
+
+    exit_on_file: Optional[str] = None
+    """Terminate the gang as soon as this path exists (process_monitor's ``--exit_on_file``)."""
+
+    start_on_file: Optional[str] = None
+    """Hold the launch until this path exists (process_monitor's ``--start_on_file``); ``job_timeout`` covers the wait."""
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # torchrun command line -> spec
@@ -218,6 +228,12 @@ class CudaPopenRequest(PopenRequest):
     master_port: int = 0
     stage_mb: int = 0
     omp_num_threads: int = 1
+    job_timeout: float = 0.0
+    exit_on_file: Optional[str] = None
+    start_on_file: Optional[str] = None
+
+
+TIMEOUT_EXIT_CODE = 34  # reference: torchx/apps/utils/process_monitor.py:16
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -392,6 +408,8 @@ class _CudaApp(_LocalAppDef):
         self.monitor: Optional[threading.Thread] = None
         self.stop_monitor = threading.Event()
         self.failure_msg = ""
+        self.deadline: Optional[float] = None  # time.monotonic() at which job_timeout expires
+        self.exit_code: Optional[int] = None   # TIMEOUT_EXIT_CODE when the supervisor ended the job
 
 
 class LocalCudaScheduler(LocalScheduler):
@@ -489,7 +507,8 @@ class LocalCudaScheduler(LocalScheduler):
                 offset += g.nproc
         return CudaPopenRequest(app_id, app_log_dir, role_params, role_log_dirs, groups=groups, max_retries=max_retries,
                                 shm_name=f"/b2_{app_id}"[:200], master_port=opts.master_port, stage_mb=opts.stage_mb,
-                                omp_num_threads=opts.omp_num_threads)
+                                omp_num_threads=opts.omp_num_threads, job_timeout=float(opts.job_timeout or 0.0),
+                                exit_on_file=opts.exit_on_file, start_on_file=opts.start_on_file)
 
     def _submit_dryrun(self, app: AppDef, cfg: LocalOpts) -> AppDryRunInfo[CudaPopenRequest]:  # type: ignore[override]
         return AppDryRunInfo(self._to_popen_request(app, cfg), lambda req: pprint.pformat(asdict(req), indent=2, width=100))
@@ -560,8 +579,12 @@ class LocalCudaScheduler(LocalScheduler):
                     app.muxes.append(mux)
             app.extra_closers.append(lambda: [m.close() for m in app.muxes])
             app.extra_closers.append(lambda: _unlink_rendezvous_blocks(req.shm_name))
-            self._spawn_attempt(app, 0)
-            app.set_state(AppState.RUNNING)
+            app.deadline = (time.monotonic() + req.job_timeout) if req.job_timeout > 0 else None
+            if req.start_on_file and not os.path.exists(req.start_on_file):
+                app.set_state(AppState.PENDING)  # the monitor thread launches the gang when the file appears
+            else:
+                self._spawn_attempt(app, 0)
+                app.set_state(AppState.RUNNING)
             self._apps[req.app_id] = app
             self._register(app)
         app.monitor = threading.Thread(target=self._monitor, args=(app,), name=f"monitor-{req.app_id}", daemon=True)
@@ -608,9 +631,29 @@ class LocalCudaScheduler(LocalScheduler):
     def _monitor(self, app: _CudaApp) -> None:
         """Gang supervision: any worker failure kills the attempt; with retries left the whole gang is re-launched
         under the next epoch (RetryPolicy.APPLICATION semantics), otherwise the app is FAILED."""
+        req = app.request
         while not app.stop_monitor.wait(MONITOR_POLL_S):
             with app.lock:
                 if is_terminal(app.state):
+                    return
+                # -- process_monitor semantics for the gang (reference torchx/apps/utils/process_monitor.py:65-118) --
+                timed_out = app.deadline is not None and time.monotonic() > app.deadline
+                if app.state == AppState.PENDING:  # start_on_file: nothing launched yet
+                    if timed_out:
+                        app.failure_msg = "reached timeout before launching"
+                        app.exit_code = TIMEOUT_EXIT_CODE
+                        app.set_state(AppState.FAILED)
+                        return
+                    if os.path.exists(req.start_on_file or ""):
+                        self._spawn_attempt(app, 0)
+                        app.set_state(AppState.RUNNING)
+                    continue
+                if timed_out or (req.exit_on_file and os.path.exists(req.exit_on_file)):
+                    app.failure_msg = (f"reached the job timeout of {req.job_timeout:g} s" if timed_out
+                                       else f"{req.exit_on_file} exists") + ": gang terminated by the scheduler"
+                    app.exit_code = TIMEOUT_EXIT_CODE
+                    app.kill()  # SIGTERM, grace period, SIGKILL
+                    app.set_state(AppState.FAILED)
                     return
                 reps = app.replicas()
                 failed = [r for r in reps if r.failed()]
