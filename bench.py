@@ -284,6 +284,8 @@ class Trainer:
         y = yh.to(self.device)
         for _ in range(warmup):
             self.step(x, y)
+        torch.cuda.synchronize()
+        nv0 = nvlink_bytes(self.device.index) if (self.rank == 0 and self.world > 1) else None  # before the barrier: see allreduce_points
         self.barrier()
         launches0 = self.comm.launches if self.comm is not None else 0
         prof = getattr(self.ddp, "start_profile", None)
@@ -306,7 +308,8 @@ class Trainer:
         elapsed = e0.elapsed_time(e1) * 1e-3
         launches = (self.comm.launches - launches0) if self.comm is not None else 0
         kernel = self.ddp.stop_profile() if prof else None
-        return elapsed, float(loss.item()), clocks, launches, kernel
+        nv1 = nvlink_bytes(self.device.index) if (self.rank == 0 and self.world > 1) else None
+        return elapsed, float(loss.item()), clocks, launches, kernel, nv0, nv1
 
     def run_e2e(self, steps, warmup):
         """`e2e`: every step's batch is copied from pinned host memory inside the timed region (double-buffered on
@@ -386,8 +389,10 @@ class Trainer:
                 for i in range(warm):
                     op(bufs[i % len(bufs)])
             stream.synchronize()
-            self.barrier()
+            # counters are read OUTSIDE the barrier-bracketed region: nvidia-smi takes ~1 s on rank 0 and the other ranks'
+            # kernels would spin on it inside their timed loop (the two barriers add a few hundred bytes of traffic)
             nv0 = nvlink_bytes(self.device.index) if self.rank == 0 else None
+            self.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(stream):
                 e0.record(stream)
@@ -395,12 +400,14 @@ class Trainer:
                     op(bufs[i % len(bufs)])
                 e1.record(stream)
             stream.synchronize()
+            algo = self.comm.last_algo if self.comm is not None else None
+            self.barrier()
             nv1 = nvlink_bytes(self.device.index) if self.rank == 0 else None
             t = self.max_over_ranks(e0.elapsed_time(e1) * 1e-3 / iters)
             row = {"bucket_mib_fp32": mib, "us": round(t * 1e6, 2), "busbw_gbs": round(2 * n / t * k / 1e9, 1),
                    "frac_of_900": round(2 * n / t * k / 1e9 / 900.0, 4)}
-            if self.comm is not None:
-                row["algo"] = self.comm.last_algo
+            if algo is not None:
+                row["algo"] = algo
             if nv0 and nv1:
                 row["nvlink_tx_bytes_per_op"] = int((nv1[0] - nv0[0]) / iters)
                 row["nvlink_rx_bytes_per_op"] = int((nv1[1] - nv0[1]) / iters)
@@ -563,9 +570,7 @@ def main():
         args.batch = spec["batch"]
     unit = spec["unit"] + "/sec"
     tr = Trainer(args, rank, world, local_rank)
-    nv0 = nvlink_bytes(local_rank) if (rank == 0 and world > 1) else None
-    elapsed, last_loss, clocks, launches, kernel = tr.run_resident(args.steps, args.warmup)
-    nv1 = nvlink_bytes(local_rank) if (rank == 0 and world > 1) else None
+    elapsed, last_loss, clocks, launches, kernel, nv0, nv1 = tr.run_resident(args.steps, args.warmup)
     elapsed = tr.max_over_ranks(elapsed)
     samples = args.batch * world * args.steps
     n_grad = int(sum(p.numel() for p in tr.ddp.parameters() if p.requires_grad))

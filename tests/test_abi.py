@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_header_constants_match_binding():
     src = open(os.path.join(ROOT, "include", "b200ddp.h")).read()
     for name in ("B2_OK", "B2_EINVAL", "B2_ECUDA", "B2_ESYS", "B2_ETIMEOUT", "B2_ENOPEER", "B2_ESTATE", "B2_F32_WIRE_BF16",
-                 "B2_F32", "B2_BF16", "B2_ALGO_AUTO", "B2_ALGO_ONESHOT", "B2_ALGO_TWOSHOT", "B2_ALGO_TWOSHOT_PIPE", "B2_ALGO_NVLS", "B2_ENOTSUP", "B2_CAP_VMM", "B2_CAP_MULTICAST", "B2_ABI_VERSION", "B2_MAX_WORLD"):
+                 "B2_F32", "B2_BF16", "B2_ALGO_AUTO", "B2_ALGO_ONESHOT", "B2_ALGO_TWOSHOT", "B2_ALGO_TWOSHOT_PIPE", "B2_ALGO_NVLS", "B2_ENOTSUP", "B2_CAP_VMM", "B2_CAP_MULTICAST", "B2_ABI_VERSION", "B2_MAX_WORLD", "B2_MAX_SEGMENTS"):
         m = re.search(rf"#define\s+{name}\s+\(?(-?\d+)\)?", src)
         assert m, name
         assert int(m.group(1)) == getattr(N, name), name
@@ -43,3 +43,12 @@ def test_argument_validation_without_a_gpu():
     assert L.b2_allreduce(None, None, 8, 0, 1.0, 0, None) == N.B2_EINVAL
     assert L.b2_comm_status(None) == N.B2_EINVAL
     assert L.b2_comm_destroy(None) == N.B2_OK
+    # the gather variant validates its segment table on the host before anything is launched
+    segs = (N.B2Segment * 2)()
+    segs[0].src, segs[0].begin, segs[0].end = 4096, 0, 10
+    segs[1].src, segs[1].begin, segs[1].end = 8192, 12, 20  # gap: does not continue at element 10
+    assert L.b2_allreduce_gather(None, ctypes.c_void_p(4096), 20, segs, 2, 0, 1.0, 0, None) == N.B2_EINVAL
+    assert b"does not continue" in L.b2_last_error()
+    assert L.b2_allreduce_gather(None, ctypes.c_void_p(4096), 20, segs, N.B2_MAX_SEGMENTS + 1, 0, 1.0, 0, None) == N.B2_EINVAL
+    assert L.b2_comm_caps(None) == N.B2_EINVAL and L.b2_comm_last_algo(None) == N.B2_EINVAL
+    assert L.b2_comm_set_param(None, b"max_ctas", 1) == N.B2_EINVAL

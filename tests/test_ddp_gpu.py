@@ -237,10 +237,16 @@ def test_zero_copy_bucket_fill_equals_copy_in(zero_copy):
                 twin = _convnet(0)
                 twin(xs[r]).square().mean().backward()
                 local.append(_flat_grads(twin))
-            for r in range(W):
+            def one_step(r, step=step, xs=xs):
+                # one host thread per rank, like the real topology: a host-side sync in one rank's step (first-use cuDNN
+                # workspace / allocator growth = cudaMalloc = device-wide sync) must not keep the other rank from launching
+                # the kernels this rank's collectives are spinning on
                 with torch.cuda.stream(streams[r]):
                     ddps[r].zero_grad(set_to_none=(step != 1))  # step 1: grads stay bucket views and accumulate in place
                     ddps[r](xs[r]).square().mean().backward()
+                    streams[r].synchronize()
+
+            _run_ranks(W, one_step)
             torch.cuda.synchronize()
             for c in comms:
                 c.check()

@@ -114,9 +114,12 @@ def main():
         row = {"bytes_fp32": S, "n": n, "world": world}
         k = 2.0 * (world - 1) / world
 
-        # parity first (one fresh buffer): ours (AUTO) vs NCCL bf16 path
-        x = bufs[0].clone()
-        y = bufs[0].clone()
+        # parity first (one fresh buffer): ours (AUTO) vs NCCL bf16 path.  `pristine` keeps the un-reduced input: the timing
+        # loops below allreduce `bufs` in place over and over (after the first pass every rank holds the same values).
+        pristine = bufs[0].clone()
+        x = pristine.clone()
+        y = pristine.clone()
+        torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             comm.allreduce_(x, stream=stream)
             c = y.to(torch.bfloat16).div_(world)
@@ -139,7 +142,8 @@ def main():
             key = f"ours[{algo},ctas={v['ctas']},chunk={v['chunk']}]"
             chk = None
             if a.check_variants:
-                xv = bufs[0].clone()
+                xv = pristine.clone()
+                torch.cuda.synchronize()
                 with torch.cuda.stream(stream):
                     comm.allreduce_(xv, algo=algo, stream=stream)
                 stream.synchronize()
@@ -206,7 +210,7 @@ def main():
         if rank == 0:
             print(json.dumps(row), flush=True)
         rows.append(row)
-        del bufs
+        del bufs, pristine, x, y
         torch.cuda.empty_cache()
     if rank == 0 and a.out:
         with open(a.out, "w") as f:

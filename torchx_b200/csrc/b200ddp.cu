@@ -184,6 +184,16 @@ void layout(b2_comm* c, int world, size_t stage_bytes) {
   c->d.stage_off[0] = kFlagRegionBytes;
   c->d.stage_off[1] = kFlagRegionBytes + c->stage_bytes;
   c->arena_bytes = kFlagRegionBytes + 2 * c->stage_bytes;
+  c->d.nvls_out_off[0] = c->d.nvls_out_off[1] = 0;
+}
+
+// NVLS output buffers (one per staging parity, W regions each = the largest message of one launch), appended to the arena
+// when the ranks agreed to try multicast.  Kept all-sentinel between collectives (CommDev::nvls_out_off).
+void layout_nvls_out(b2_comm* c) {
+  const size_t bytes = static_cast<size_t>(c->d.world) * c->d.slice_cap;
+  c->d.nvls_out_off[0] = c->arena_bytes;
+  c->d.nvls_out_off[1] = c->arena_bytes + bytes;
+  c->arena_bytes += 2 * bytes;
 }
 
 // Everything of a rank except the arena itself.
@@ -198,8 +208,10 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   layout(c, world, stage_bytes);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
-  c->pipe_min_wire_bytes = env_size("B2_PIPE_MIN_BYTES", 2u << 20);
-  c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 1u << 20);
+  // Provisional AUTO thresholds (8xB200, profiles/r02_sweep_w8.md): the single-pass two-shot kernel wins up to ~256 MiB of
+  // wire data; the NVLS path only overtakes it for the largest messages.
+  c->pipe_min_wire_bytes = env_size("B2_PIPE_MIN_BYTES", ~static_cast<size_t>(0));
+  c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 256u << 20);
   c->nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 4));
   c->pipe_chunk_bytes = env_size("B2_PIPE_CHUNK_KB", 2048) << 10;
   B2_CUDA(cudaSetDevice(device));
@@ -220,6 +232,7 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
 int alloc_arena(b2_comm* c, bool use_vmm, bool multicast, const int* devices, int ndev) {
   B2_CUDA(cudaSetDevice(c->device));
   c->use_vmm = use_vmm;
+  if (multicast) layout_nvls_out(c);
   if (use_vmm) {
     const size_t gran = vmm::arena_granularity(c->device, c->d.world, multicast);
     c->arena_bytes = (c->arena_bytes + gran - 1) / gran * gran;
@@ -233,6 +246,8 @@ int alloc_arena(b2_comm* c, bool use_vmm, bool multicast, const int* devices, in
     B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
   }
   B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
+  if (c->d.nvls_out_off[0] != 0)
+    B2_CUDA(cudaMemset(static_cast<uint8_t*>(c->arena) + c->d.nvls_out_off[0], 0xFF, 2 * static_cast<size_t>(c->d.world) * c->d.slice_cap));
   B2_CUDA(cudaDeviceSynchronize());
   c->arena_of[c->d.rank] = static_cast<uint8_t*>(c->arena);
   return B2_OK;

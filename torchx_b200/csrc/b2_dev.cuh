@@ -27,6 +27,10 @@ constexpr size_t kDefaultStageBytes = 512ull << 20;  // x2 stages = 1 GiB of the
 // stall of a healthy peer (rank-0 checkpoint / eval, a dataloader hiccup): NCCL's default for the same situation is 600 s.
 constexpr unsigned long long kDefaultTimeoutNs = 600ull * 1000ull * 1000ull * 1000ull;
 
+// "Not written yet" marker of the NVLS output buffers: a 32-bit word that reduced data never contains (as two bf16 lanes or
+// as one fp32 it is a NaN with an all-ones payload; the producer canonicalises such a word to the default NaN first).
+constexpr uint32_t kSentinel = 0xFFFFFFFFu;
+
 static_assert(kMaxCtas * kFlagSlotBytes <= (int)kXbarFlagBytes, "xbar flag region too small");
 static_assert((size_t)kMaxCtas * kPipeKinds * kMaxChunks * kFlagSlotBytes <= kPipeFlagBytes, "pipeline flag region too small");
 
@@ -53,6 +57,10 @@ struct CommDev {
   unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
                                     //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced";
                                     //   the NVLS path uses regions 0..W-1 as ONE contiguous message-sized buffer
+  unsigned long long nvls_out_off[2];  // NVLS only: per staging parity, a message-sized buffer the switch multicasts the
+                                    // reduced slices into.  Always all-SENTINEL outside a running NVLS collective: consumers
+                                    // recognise arrived data by "not the sentinel" (no fence, no barrier) and put the
+                                    // sentinel back after reading
   unsigned long long* trace;        // optional (b2_comm_trace): per-CTA globaltimer stamps of the LAST collective,
                                     // 8 slots per CTA (see include/b200ddp.h)
 };
@@ -159,6 +167,29 @@ __device__ __forceinline__ void mm_st_u4(void* p, const uint4& r) {
                : "memory");
 }
 
+// 16-byte load that always goes to L2 (polling for data another GPU / the switch writes): LDG.E.128.STRONG.SYS
+__device__ __forceinline__ uint4 ld_volatile_u4(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ bool has_sentinel(const uint4& q) {
+  return q.x == kSentinel || q.y == kSentinel || q.z == kSentinel || q.w == kSentinel;
+}
+// reduced data never carries the sentinel: an all-ones NaN word becomes the default NaN (bf16x2: both lanes)
+template <bool F32>
+__device__ __forceinline__ uint4 no_sentinel(uint4 q) {
+  constexpr uint32_t kNan = F32 ? 0x7FFFFFFFu : 0x7FFF7FFFu;
+  if (q.x == kSentinel) q.x = kNan;
+  if (q.y == kSentinel) q.y = kNan;
+  if (q.z == kSentinel) q.z = kNan;
+  if (q.w == kSentinel) q.w = kNan;
+  return q;
+}
+
 // fp32 pair -> packed bf16x2 with round-to-nearest-even (one F2FP.BF16.F32.PACK_AB). `lo` lands
 // in bits [15:0] (the lower address in little-endian memory), `hi` in bits [31:16].
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -238,6 +269,56 @@ __device__ __forceinline__ void mm_st_wire(uint8_t* p, const Wire<MODE>& w) {
   } else {
     mm_st_u4(p, w.q);
   }
+}
+
+// ---- sentinel protocol of the NVLS output buffer (see CommDev::nvls_out_off) -----------------------------------------
+template <int MODE>
+__device__ __forceinline__ Wire<MODE> wire_no_sentinel(Wire<MODE> w) {
+  if constexpr (MODE == B2_F32) {
+    uint4 a = make_uint4(__float_as_uint(w.f.v[0]), __float_as_uint(w.f.v[1]), __float_as_uint(w.f.v[2]), __float_as_uint(w.f.v[3]));
+    uint4 b = make_uint4(__float_as_uint(w.f.v[4]), __float_as_uint(w.f.v[5]), __float_as_uint(w.f.v[6]), __float_as_uint(w.f.v[7]));
+    a = no_sentinel<true>(a);
+    b = no_sentinel<true>(b);
+    w.f.v[0] = __uint_as_float(a.x);
+    w.f.v[1] = __uint_as_float(a.y);
+    w.f.v[2] = __uint_as_float(a.z);
+    w.f.v[3] = __uint_as_float(a.w);
+    w.f.v[4] = __uint_as_float(b.x);
+    w.f.v[5] = __uint_as_float(b.y);
+    w.f.v[6] = __uint_as_float(b.z);
+    w.f.v[7] = __uint_as_float(b.w);
+  } else {
+    w.q = no_sentinel<false>(w.q);
+  }
+  return w;
+}
+// One poll of a wire vec in the output buffer; `pending` = some 32-bit word still holds the sentinel (a 16-byte multicast
+// store lands as a whole, but every word is checked anyway).
+template <int MODE>
+__device__ __forceinline__ Wire<MODE> wire_poll(const uint8_t* p, bool* pending) {
+  Wire<MODE> w;
+  if constexpr (MODE == B2_F32) {
+    const uint4 a = ld_volatile_u4(p), b = ld_volatile_u4(p + 16);
+    *pending = has_sentinel(a) || has_sentinel(b);
+    w.f.v[0] = __uint_as_float(a.x);
+    w.f.v[1] = __uint_as_float(a.y);
+    w.f.v[2] = __uint_as_float(a.z);
+    w.f.v[3] = __uint_as_float(a.w);
+    w.f.v[4] = __uint_as_float(b.x);
+    w.f.v[5] = __uint_as_float(b.y);
+    w.f.v[6] = __uint_as_float(b.z);
+    w.f.v[7] = __uint_as_float(b.w);
+  } else {
+    w.q = ld_volatile_u4(p);
+    *pending = has_sentinel(w.q);
+  }
+  return w;
+}
+template <int MODE>
+__device__ __forceinline__ void wire_reset(uint8_t* p) {
+  const uint4 s4 = make_uint4(kSentinel, kSentinel, kSentinel, kSentinel);
+  stg_u4(p, s4);
+  if constexpr (MODE == B2_F32) stg_u4(p + 16, s4);
 }
 
 // wire(scale * x): the value a rank contributes.  Rounding points are part of the contract

@@ -10,8 +10,11 @@
 //   NVLS  (k_pipe<.., kNvls>; needs the multicast mapping of the arena):
 //     A cast   : read my fp32 bucket once, cast+scale, store bf16 into MY stage (local HBM/L2)        -> signal X1[k]
 //     B move   : wait X1[k] from all ranks; multimem.ld_reduce my slice (the SWITCH sums the W stages, fp32 accumulate,
-//                one rounding) and multimem.st the result back to every rank's stage (in place)       -> signal X2[k]
-//     C widen  : wait X2[k] from all ranks; read my stage (all W slices, now reduced), widen, write my bucket
+//                one rounding) and multimem.st the result into every rank's OUTPUT buffer          -> un-fenced hint X2[k]
+//     C widen  : wait for the hint; read my output buffer (all W slices), validating every vec against the SENTINEL the
+//                buffer is kept filled with (a vec is there when it no longer holds the sentinel: no release fence, no
+//                second barrier - the ~8 us drain of the multicast stores disappears from the critical path), widen,
+//                write my bucket, put the sentinel back
 //     NVLink traffic per GPU and direction: (1 + 1/W) * S instead of the 2 (W-1)/W * S of any P2P algorithm.
 //
 //   P2P   (k_pipe<.., kP2p>; any world, plain peer mappings):
@@ -71,20 +74,37 @@ __device__ __forceinline__ void chunk_done(int id, int count, int t, uint32_t* b
   if (t == 0) mail_post(box, static_cast<uint32_t>(k + 1));
 }
 // Signaller warp of a role: publish chunks 0..nk-1 of `kind` to every rank as the data warps complete them.
-// Lane l (< world) pairs with rank (rank + l) % world and writes word [my rank] of that rank's slot.
+// Lane l (< world) pairs with rank (rank + l) % world and writes word [my rank] of that rank's slot.  ONE release fence
+// covers every chunk the data warps have finished by the time the signaller looks (a fence after a burst of stores takes
+// ~8 us - the drain of the memory system's backlog - and fences of one warp do not overlap): the pipeline granularity
+// adapts to the fence latency instead of serialising K fences.
+template <bool FENCE>
 __device__ __forceinline__ void signaller(const CommDev& c, int lane, const uint32_t* box, int kind, int nk, uint32_t seq) {
-  for (int k = 0; k < nk; ++k) {
+  int k = 0;
+  while (k < nk) {
     unsigned long long t0 = 0;
     unsigned spins = 0;
-    while (mail_peek(box) < static_cast<uint32_t>(k + 1)) {  // chunk k not finished by the data warps yet
+    uint32_t done;
+    while ((done = mail_peek(box)) < static_cast<uint32_t>(k + 1)) {  // chunk k not finished by the data warps yet
       if ((++spins & 1023u) == 0) {
         const unsigned long long now = dev::globaltimer_ns();
         if (t0 == 0) t0 = now;
-        else if (now - t0 > c.timeout_ns) break;  // the data warps are stuck behind a dead peer: they report it themselves
+        else if (now - t0 > c.timeout_ns) {  // the data warps are stuck behind a dead peer: they report it themselves
+          done = static_cast<uint32_t>(nk);
+          break;
+        }
       }
     }
     __syncwarp();
-    if (lane < c.world) dev::st_release_sys(flag_slot(dev::peer_sel(c, lane), c, kind, k) + c.rank, seq);
+    if (lane < c.world) {
+      // everything the data warps stored for chunks < done is ordered first - unless the flag is only a HINT (NVLS X2: the
+      // consumer validates every vec against the sentinel itself, the flag just tells it when polling becomes worthwhile)
+      if constexpr (FENCE) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      uint8_t* their = dev::peer_sel(c, lane);
+      for (int kk = k; kk < static_cast<int>(done); ++kk)
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(flag_slot(their, c, kind, kk) + c.rank), "r"(seq) : "memory");
+    }
+    k = static_cast<int>(done);
   }
 }
 // Wait until every rank has published `seq` for (kind, k): thread t (< world) polls word [t] of my own slot.
@@ -111,6 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long Ls = (V + W - 1) / W;
   const unsigned long long g = gridDim.x, b = blockIdx.x;
   const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;  // P2P only
+  const unsigned long long nvls_out = (seq0 & 1u) ? c.nvls_out_off[1] : c.nvls_out_off[0];        // NVLS only
   uint8_t* const mine = c.peer[0];
   const int tid = threadIdx.x;
   // chunks this CTA really has: cell (k, b) starts at (k*g + b)*cell, empty from the first k with start >= Ls on
@@ -161,7 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (t == 0) trace_stamp(c, 1);
   } else if (tid < kB0) {
-    signaller(c, tid - kAS, &mail[0], 0, nk, seq);  // role A's signaller: X1[k]
+    signaller<true>(c, tid - kAS, &mail[0], 0, nk, seq);  // role A's signaller: X1[k]
   } else if (tid < kBS) {
     // ================= role B data: move (NVLS) / reduce (P2P) =================
     const int t = tid - kB0;
@@ -173,18 +194,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (t == 0 && k == 0) trace_stamp(c, 2);
       if constexpr (ALG == kNvls) {
         constexpr int UM = MODE == B2_F32 ? 4 : 8;  // 128 B of switch-side reductions in flight per thread
-        uint8_t* const mcs = c.mc + stage;
+        const uint8_t* const mc_in = c.mc + stage;   // every rank's staged contribution, summed by the switch on load
+        uint8_t* const mc_out = c.mc + nvls_out;     // every rank's output buffer, written by the switch on store
         for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kBD) * UM) {
           Wire<MODE> q[UM];
 #pragma unroll
           for (int u = 0; u < UM; ++u) {
             const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
-            if (v < hi && base + v < V) q[u] = mm_ld_reduce_wire<MODE>(mcs + (base + v) * WVB);
+            if (v < hi && base + v < V) q[u] = mm_ld_reduce_wire<MODE>(mc_in + (base + v) * WVB);
           }
 #pragma unroll
           for (int u = 0; u < UM; ++u) {
             const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
-            if (v < hi && base + v < V) mm_st_wire<MODE>(mcs + (base + v) * WVB, q[u]);
+            if (v < hi && base + v < V) mm_st_wire<MODE>(mc_out + (base + v) * WVB, wire_no_sentinel<MODE>(q[u]));
           }
         }
       } else {
@@ -214,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     if (t == 0) trace_stamp(c, 3);
   } else if (tid < kC0) {
-    signaller(c, tid - kBS, &mail[1], 1, nk, seq);  // role B's signaller: X2[k]
+    signaller<ALG != kNvls>(c, tid - kBS, &mail[1], 1, nk, seq);  // role B's signaller: X2[k] (NVLS: un-fenced hint)
   } else {
     // ================= role C: widen (NVLS) / gather (P2P) =================
     const int t = tid - kC0;
@@ -225,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (t == 0 && k == 0) trace_stamp(c, 4);
       for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kCD) * U) {
         Wire<MODE> w[U][W];
+        bool pend[U][W];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kCD;
@@ -233,11 +256,42 @@ __global__ void __launch_bounds__(kThreads, 1)
             int j = c.rank + jj;
             if (j >= W) j -= W;
             const unsigned long long gv = j * Ls + v;
+            pend[u][jj] = false;
             if (v < hi && gv < V) {
               if constexpr (ALG == kNvls)
-                w[u][jj] = ld_wire<MODE>(mine + stage + gv * WVB);  // the switch replicated every slice into my stage
+                w[u][jj] = wire_poll<MODE>(mine + nvls_out + gv * WVB, &pend[u][jj]);  // the switch multicasts every slice here
               else
                 w[u][jj] = ld_wire<MODE>(c.peer[jj] + reduced + v * WVB);  // rank j's reduced slice, over NVLink
+            }
+          }
+        }
+        if constexpr (ALG == kNvls) {
+          // data the hint ran ahead of: poll until the sentinel is gone (bounded like every other wait)
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kCD;
+#pragma unroll
+            for (int jj = 0; jj < W; ++jj) {
+              if (!pend[u][jj]) continue;
+              int j = c.rank + jj;
+              if (j >= W) j -= W;
+              const uint8_t* p = mine + nvls_out + (j * Ls + v) * WVB;
+              unsigned long long t0 = 0;
+              unsigned spins = 0;
+              bool pending = true;
+              while (pending) {
+                __nanosleep(64);
+                w[u][jj] = wire_poll<MODE>(p, &pending);
+                if (pending && (++spins & 63u) == 0) {
+                  const unsigned long long now = globaltimer_ns();
+                  if (t0 == 0) t0 = now;
+                  else if (now - t0 > c.timeout_ns) {
+                    *reinterpret_cast<volatile uint32_t*>(c.status) = static_cast<uint32_t>(-B2_ETIMEOUT);
+                    __threadfence_system();
+                    break;
+                  }
+                }
+              }
             }
           }
         }
@@ -249,7 +303,10 @@ __global__ void __launch_bounds__(kThreads, 1)
             int j = c.rank + jj;
             if (j >= W) j -= W;
             const unsigned long long gv = j * Ls + v;
-            if (v < hi && gv < V) store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
+            if (v < hi && gv < V) {
+              store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
+              if constexpr (ALG == kNvls) wire_reset<MODE>(mine + nvls_out + gv * WVB);  // back to "not written yet"
+            }
           }
         }
       }
