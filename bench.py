@@ -427,7 +427,7 @@ class Trainer:
         import oracle
 
         torch, W = self.torch, self.world
-        algos = ["auto", "oneshot", "twoshot", "twoshot_pipe"] + (["nvls"] if self.comm.has_multicast else [])
+        algos = ["auto", "oneshot", "twoshot", "twoshot_ll", "twoshot_pipe"] + (["nvls"] if self.comm.has_multicast else [])
         sizes = sorted(set(self.bucket_sizes))
         if len(sizes) > 5:
             sizes = [sizes[0], statistics.median_low(self.bucket_sizes), sizes[-1]]

@@ -28,7 +28,7 @@ def emit(**kw):
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", default="bert", choices=["bert", "mlp"])
-    ap.add_argument("--impl", default="b200", choices=["b200", "nccl"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "nccl", "gloo"])
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--fail-rank", type=int, default=1)
@@ -44,6 +44,12 @@ def main() -> None:
 
         device = init_pg("b200")
         comm = communicator()
+    elif a.impl == "gloo":  # CPU plumbing check of this script and of tools/elastic_recover.py (no GPU)
+        import torch.distributed as dist
+
+        device = torch.device("cpu")
+        dist.init_process_group("gloo")
+        comm = None
     else:
         import torch.distributed as dist
         from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
@@ -66,11 +72,14 @@ def main() -> None:
         model = nn.Sequential(nn.Linear(256, 1024), nn.ReLU(), nn.Linear(1024, 1024), nn.ReLU(), nn.Linear(1024, 10)).to(device)
     if a.impl == "b200":
         ddp = DistributedDataParallel(model, comm)
+    elif a.impl == "gloo":
+        ddp = torch.nn.parallel.DistributedDataParallel(model)
     else:
         ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[device.index])
         ddp.register_comm_hook(None, default_hooks.bf16_compress_hook)
     opt = torch.optim.AdamW(ddp.parameters(), lr=1e-4)
     gen = torch.Generator(device=device).manual_seed(99 + rank)
+    sync = (lambda: torch.cuda.synchronize(device)) if device.type == "cuda" else (lambda: None)
     emit(event="model_ready", rank=rank, attempt=attempt, t=time.time())
     for step in range(a.steps):
         if attempt == 0 and not a.no_fail and rank == a.fail_rank and step == a.fail_at_step:
@@ -88,7 +97,7 @@ def main() -> None:
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
-        torch.cuda.synchronize(device)
+        sync()
         emit(event="step", rank=rank, attempt=attempt, step=step, t=time.time(), loss=round(float(loss.item()), 4))
     if comm is not None:
         comm.check()

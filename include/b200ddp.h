@@ -70,6 +70,9 @@ extern "C" {
 #define B2_ALGO_NVLS 4         /* cast -> multimem.ld_reduce + multimem.st through the NVSwitch -> widen, pipelined;
                                   needs B2_CAP_MULTICAST.  The switch sums the W contributions with fp32 accumulation
                                   and rounds once; its summation order is the switch's, see DESIGN.md 2.4              */
+#define B2_ALGO_TWOSHOT_LL 5   /* barrier-free two-shot: push-scatter -> reduce as contributions arrive -> push the result
+                                  to every rank -> widen as slices arrive; arrival is read off the data itself (sentinel-
+                                  filled buffers), no flag barrier and no fence on the data path; rank-order arithmetic   */
 
 /* ---- capabilities (b2_comm_caps) -------------------------------------------------- */
 #define B2_CAP_VMM 1       /* arena is a CUDA VMM allocation shared by file descriptor (else cudaMalloc + CUDA IPC) */
@@ -125,6 +128,7 @@ int b2_comm_set_max_ctas(b2_comm_t* comm, int max_ctas);
  *   "pipe_min_bytes"     pipelined two-shot from this many wire bytes   (env B2_PIPE_MIN_BYTES)
  *   "nvls_min_bytes"     NVLS from this many wire bytes                 (env B2_NVLS_MIN_BYTES)
  *   "nvls_min_world"     NVLS from this world size                      (env B2_NVLS_MIN_WORLD)
+ *   "ll_min_bytes"       barrier-free LL two-shot from this many wire bytes (env B2_LL_MIN_BYTES)
  *   "pipe_chunk_bytes"   target wire bytes per pipeline chunk           (env B2_PIPE_CHUNK_KB, in KiB)
  *   "max_ctas"           same as b2_comm_set_max_ctas
  */

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_header_constants_match_binding():
     src = open(os.path.join(ROOT, "include", "b200ddp.h")).read()
     for name in ("B2_OK", "B2_EINVAL", "B2_ECUDA", "B2_ESYS", "B2_ETIMEOUT", "B2_ENOPEER", "B2_ESTATE", "B2_F32_WIRE_BF16",
-                 "B2_F32", "B2_BF16", "B2_ALGO_AUTO", "B2_ALGO_ONESHOT", "B2_ALGO_TWOSHOT", "B2_ALGO_TWOSHOT_PIPE", "B2_ALGO_NVLS", "B2_ENOTSUP", "B2_CAP_VMM", "B2_CAP_MULTICAST", "B2_ABI_VERSION", "B2_MAX_WORLD", "B2_MAX_SEGMENTS"):
+                 "B2_F32", "B2_BF16", "B2_ALGO_AUTO", "B2_ALGO_ONESHOT", "B2_ALGO_TWOSHOT", "B2_ALGO_TWOSHOT_PIPE", "B2_ALGO_NVLS", "B2_ALGO_TWOSHOT_LL", "B2_ENOTSUP", "B2_CAP_VMM", "B2_CAP_MULTICAST", "B2_ABI_VERSION", "B2_MAX_WORLD", "B2_MAX_SEGMENTS"):
         m = re.search(rf"#define\s+{name}\s+\(?(-?\d+)\)?", src)
         assert m, name
         assert int(m.group(1)) == getattr(N, name), name

@@ -106,7 +106,7 @@ def test_local_pass_matches_oracle(mode):
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe", "twoshot_ll"])
 def test_allreduce_matches_oracle_one_device(world, mode, algo):
     w = World([0] * world)
     try:
@@ -128,6 +128,8 @@ def test_allreduce_auto_and_chunking(world):
             _check_allreduce(w, n, "f32_wire_bf16", "auto", "randn", seed=n)
         _check_allreduce(w, (1 << 19) + 3, "f32", "twoshot", "randn", seed=5)
         _check_allreduce(w, (1 << 20) + 9, "f32_wire_bf16", "twoshot_pipe", "special", seed=6)
+        _check_allreduce(w, (1 << 20) + 11, "f32_wire_bf16", "twoshot_ll", "special", seed=7)
+        _check_allreduce(w, (1 << 19) + 7, "bf16", "twoshot_ll", "randn", seed=8)
     finally:
         w.close()
 
@@ -158,7 +160,7 @@ def test_back_to_back_ops_reuse_staging_safely():
     try:
         for c in w.comms:
             c.set_param("pipe_chunk_bytes", 1 << 10)
-        plan = [(1000 + 37 * i, ("oneshot", "twoshot", "twoshot_pipe")[i % 3]) for i in range(42)]
+        plan = [(1000 + 37 * i, ("oneshot", "twoshot", "twoshot_pipe", "twoshot_ll", "twoshot_ll")[i % 5]) for i in range(45)]
         tens = [[None] * len(plan) for _ in range(W)]
         wants = []
         for k, (n, _) in enumerate(plan):
@@ -234,7 +236,7 @@ def test_dead_peer_times_out_instead_of_hanging():
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe", "nvls", "auto"])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "twoshot_pipe", "twoshot_ll", "nvls", "auto"])
 def test_allreduce_across_devices(world, algo, cuda_count):
     """Real NVLink/NVSwitch peers (skipped on a 1-GPU box).  In-process worlds over distinct devices use the VMM arena and,
     where the fabric offers it, the multicast object - the same mappings as the one-process-per-GPU path minus fd passing."""
@@ -267,7 +269,7 @@ def test_messages_larger_than_a_stage_across_devices(world, cuda_count):
     try:
         for c in w.comms:
             c.set_param("pipe_chunk_bytes", 32 << 10)
-        algos = ["twoshot", "twoshot_pipe", "oneshot"] + (["nvls"] if w.comms[0].has_multicast else [])
+        algos = ["twoshot", "twoshot_pipe", "twoshot_ll", "oneshot"] + (["nvls"] if w.comms[0].has_multicast else [])
         for algo in algos:
             before = w.comms[0].launches
             _check_allreduce(w, (3 << 20) + 17, "f32_wire_bf16", algo, "special", seed=5)

@@ -42,6 +42,7 @@ def _run_world(world, devices, tmp_path, n=100003):
             xs = make_inputs(world, n, 10 + k, "special")
             assert_bits_equal(got[f"ar{k}"], oracle.allreduce(mode, xs, 1.0 / world), f"rank {r} op {k}")
         assert np.all(got["bcast"] == float(world)), r
+        assert_bits_equal(got["ll"], oracle.allreduce(oracle.B2O_F32_WIRE_BF16, make_inputs(world, n, 30, "special"), 1.0 / world), f"rank {r} LL two-shot")
         if "nvls" in got.files:  # the box exposes NVSwitch multicast: the worker also ran the NVLS algorithm
             assert_nvls_result(got["nvls"], make_inputs(world, n, 20, "randn"), 1.0 / world, oracle.B2O_F32_WIRE_BF16, f"nvls rank {r}")
     return int(np.load(tmp_path / "r0.npz")["caps"][0])

@@ -36,6 +36,12 @@ def main() -> None:
         t = torch.from_numpy(x).to(f"cuda:{a.device}")
         comm.allreduce_(t, wire=mode, algo=algo)
         results[f"ar{k}"] = t.cpu().numpy()
+    x = make_inputs(a.world, a.n, 30, "special")[a.rank]
+    t = torch.from_numpy(x).to(f"cuda:{a.device}")
+    for _ in range(3):  # back to back on the same buffers: the sentinel reset / parity double-buffering / flow control
+        t.copy_(torch.from_numpy(x))
+        comm.allreduce_(t, wire="bf16", algo="twoshot_ll")
+    results["ll"] = t.cpu().numpy()
     results["caps"] = np.array([comm.caps])
     if comm.has_multicast:  # NVLS through the multi-process multicast bring-up (fd passing, AddDevice / BindMem handshake)
         x = make_inputs(a.world, a.n, 20, "randn")[a.rank]

@@ -58,9 +58,10 @@ def main():
     ap.add_argument("--fail-at-step", type=int, default=30)
     ap.add_argument("--log-dir", default="/tmp/elastic_logs")
     ap.add_argument("--out", default="")
+    ap.add_argument("--impl", default="", help="override the worker implementation (gloo = CPU plumbing check)")
     a = ap.parse_args()
     script = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "train_elastic.py")
-    impl = "b200" if a.sched == "local_cuda" else "nccl"
+    impl = a.impl or ("b200" if a.sched == "local_cuda" else "nccl")
     role = "train_elastic"
     base = ["-j", f"1x{a.nproc}", "--script", script]
     sargs = ["--model", a.model, "--impl", impl, "--steps", str(a.steps), "--batch", str(a.batch), "--fail-at-step", str(a.fail_at_step)]

@@ -64,6 +64,7 @@ def parse_variant(v):
 
 
 TRACE_NAMES = {
+    "twoshot_ll": (["flow_control", "scatter_issue", "reduce_push", "(unused)", "widen"], 5),
     "oneshot": (["push", "bar1", "reduce"], 3),
     "twoshot": (["scatter", "bar1", "reduce", "bar2", "gather"], 5),
 }

@@ -26,6 +26,7 @@
 #include "b2_dev.cuh"
 #include "b2_kernels.cuh"
 #include "b2_pipe.cuh"
+#include "b2_ll.cuh"
 #include "b2_vmm.h"
 
 #include <errno.h>
@@ -147,6 +148,7 @@ struct b2_comm {
   size_t pipe_min_wire_bytes = 0;     // AUTO: the pipelined kernels from this many wire bytes
   size_t nvls_min_wire_bytes = 0;     // AUTO: NVLS (when available and the mode allows it) from this many wire bytes
   int nvls_min_world = 4;             // AUTO: NVLS only pays once (1 + 1/W) < 2 (W-1)/W, i.e. W >= 4
+  size_t ll_min_wire_bytes = 0;       // AUTO: the barrier-free LL two-shot from this many wire bytes
   size_t pipe_chunk_bytes = 0;        // target wire bytes of one pipeline chunk (per rank)
   uint64_t launches = 0;
   int last_algo = 0;                  // B2_ALGO_* of the most recent allreduce launch (what AUTO picked)
@@ -184,16 +186,12 @@ void layout(b2_comm* c, int world, size_t stage_bytes) {
   c->d.stage_off[0] = kFlagRegionBytes;
   c->d.stage_off[1] = kFlagRegionBytes + c->stage_bytes;
   c->arena_bytes = kFlagRegionBytes + 2 * c->stage_bytes;
-  c->d.nvls_out_off[0] = c->d.nvls_out_off[1] = 0;
-}
-
-// NVLS output buffers (one per staging parity, W regions each = the largest message of one launch), appended to the arena
-// when the ranks agreed to try multicast.  Kept all-sentinel between collectives (CommDev::nvls_out_off).
-void layout_nvls_out(b2_comm* c) {
-  const size_t bytes = static_cast<size_t>(c->d.world) * c->d.slice_cap;
-  c->d.nvls_out_off[0] = c->arena_bytes;
-  c->d.nvls_out_off[1] = c->arena_bytes + bytes;
-  c->arena_bytes += 2 * bytes;
+  // the sentinel-managed buffers (LL two-shot recv/out, NVLS out): 2W regions per parity
+  const size_t ll_bytes = 2 * static_cast<size_t>(world) * cap;
+  c->d.ll_off[0] = c->arena_bytes;
+  c->d.ll_off[1] = c->arena_bytes + ll_bytes;
+  c->arena_bytes += 2 * ll_bytes;
+  c->d.llflag_off = 32u << 10;  // inside the xbar flag region, past its kMaxCtas slots
 }
 
 // Everything of a rank except the arena itself.
@@ -213,6 +211,7 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   c->pipe_min_wire_bytes = env_size("B2_PIPE_MIN_BYTES", ~static_cast<size_t>(0));
   c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 256u << 20);
   c->nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 4));
+  c->ll_min_wire_bytes = env_size("B2_LL_MIN_BYTES", ~static_cast<size_t>(0));
   c->pipe_chunk_bytes = env_size("B2_PIPE_CHUNK_KB", 2048) << 10;
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->counters, 256));
@@ -232,7 +231,6 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
 int alloc_arena(b2_comm* c, bool use_vmm, bool multicast, const int* devices, int ndev) {
   B2_CUDA(cudaSetDevice(c->device));
   c->use_vmm = use_vmm;
-  if (multicast) layout_nvls_out(c);
   if (use_vmm) {
     const size_t gran = vmm::arena_granularity(c->device, c->d.world, multicast);
     c->arena_bytes = (c->arena_bytes + gran - 1) / gran * gran;
@@ -246,8 +244,7 @@ int alloc_arena(b2_comm* c, bool use_vmm, bool multicast, const int* devices, in
     B2_CUDA(cudaMalloc(&c->arena, c->arena_bytes));
   }
   B2_CUDA(cudaMemset(c->arena, 0, kFlagRegionBytes));
-  if (c->d.nvls_out_off[0] != 0)
-    B2_CUDA(cudaMemset(static_cast<uint8_t*>(c->arena) + c->d.nvls_out_off[0], 0xFF, 2 * static_cast<size_t>(c->d.world) * c->d.slice_cap));
+  B2_CUDA(cudaMemset(static_cast<uint8_t*>(c->arena) + c->d.ll_off[0], 0xFF, 4 * static_cast<size_t>(c->d.world) * c->d.slice_cap));
   B2_CUDA(cudaDeviceSynchronize());
   c->arena_of[c->d.rank] = static_cast<uint8_t*>(c->arena);
   return B2_OK;
@@ -335,6 +332,11 @@ cudaError_t launch_twoshot(const CommDev& d, const Src& src, int grid, void* buf
   k_twoshot<MODE, W><<<grid, kThreads, 0, s>>>(d, src, buf, n, scale);
   return cudaGetLastError();
 }
+template <int MODE, int W>
+cudaError_t launch_ll(const CommDev& d, const Src& src, int grid, void* buf, unsigned long long n, float scale, cudaStream_t s) {
+  k_ll<MODE, W><<<grid, kThreads, 0, s>>>(d, src, buf, n, scale);
+  return cudaGetLastError();
+}
 template <int MODE, int W, int ALG>
 cudaError_t launch_pipe(const CommDev& d, const Src& src, const PipePlan& p, void* buf, unsigned long long n, float scale,
                         cudaStream_t s) {
@@ -355,6 +357,8 @@ cudaError_t launch_by_world(const CommDev& d, const Src& src, int kind, int grid
         return launch_twoshot<MODE, Wv>(d, src, grid, buf, n, scale, s);                                  \
       case B2_ALGO_TWOSHOT_PIPE:                                                                     \
         return launch_pipe<MODE, Wv, pl::kP2p>(d, src, p, buf, n, scale, s);                            \
+      case B2_ALGO_TWOSHOT_LL:                                                                       \
+        return launch_ll<MODE, Wv>(d, src, grid, buf, n, scale, s);                                  \
       default:                                                                                       \
         return launch_pipe<MODE, Wv, pl::kNvls>(d, src, p, buf, n, scale, s);                           \
     }
@@ -920,6 +924,7 @@ int b2_comm_set_param(b2_comm_t* c, const char* name, long long value) {
   else if (k == "pipe_min_bytes") c->pipe_min_wire_bytes = static_cast<size_t>(value);
   else if (k == "nvls_min_bytes") c->nvls_min_wire_bytes = static_cast<size_t>(value);
   else if (k == "nvls_min_world") c->nvls_min_world = static_cast<int>(value);
+  else if (k == "ll_min_bytes") c->ll_min_wire_bytes = static_cast<size_t>(value);
   else if (k == "pipe_chunk_bytes") c->pipe_chunk_bytes = static_cast<size_t>(value);
   else if (k == "max_ctas") c->max_ctas = static_cast<int>(value);
   else return fail(B2_EINVAL, "b2_comm_set_param: unknown parameter '%s'", name);
@@ -960,7 +965,7 @@ static int allreduce_impl(b2_comm_t* c, Src& src, void* buf, size_t n_elems, int
   if (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16)
     return fail(B2_EINVAL, "unknown mode %d", mode);
   if (algo != B2_ALGO_AUTO && algo != B2_ALGO_ONESHOT && algo != B2_ALGO_TWOSHOT && algo != B2_ALGO_TWOSHOT_PIPE &&
-      algo != B2_ALGO_NVLS)
+      algo != B2_ALGO_NVLS && algo != B2_ALGO_TWOSHOT_LL)
     return fail(B2_EINVAL, "unknown algo %d", algo);
   if (n_elems == 0) return B2_OK;
   if (!buf) return fail(B2_EINVAL, "b2_allreduce: null buffer");
@@ -992,6 +997,8 @@ static int allreduce_impl(b2_comm_t* c, Src& src, void* buf, size_t n_elems, int
         kind = B2_ALGO_NVLS;
       else if (wire_left <= c->oneshot_max_wire_bytes && V_left <= cap_vecs)
         kind = B2_ALGO_ONESHOT;
+      else if (wire_left >= c->ll_min_wire_bytes)
+        kind = B2_ALGO_TWOSHOT_LL;
       else if (wire_left >= c->pipe_min_wire_bytes)
         kind = B2_ALGO_TWOSHOT_PIPE;
       else

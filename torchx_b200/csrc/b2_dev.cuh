@@ -57,10 +57,16 @@ struct CommDev {
   unsigned long long slice_cap;     // bytes of one region; a stage is (world + 1) regions:
                                     //   regions 0..W-1 = "recv[r]" (written by rank r), region W = "reduced";
                                     //   the NVLS path uses regions 0..W-1 as ONE contiguous message-sized buffer
-  unsigned long long nvls_out_off[2];  // NVLS only: per staging parity, a message-sized buffer the switch multicasts the
-                                    // reduced slices into.  Always all-SENTINEL outside a running NVLS collective: consumers
-                                    // recognise arrived data by "not the sentinel" (no fence, no barrier) and put the
-                                    // sentinel back after reading
+  unsigned long long ll_off[2];     // per staging parity, the SENTINEL-managed buffers: 2W regions of slice_cap bytes,
+                                    //   regions 0..W-1   "recv[r]"  contributions to my slice, pushed by rank r   (LL two-shot)
+                                    //   regions W..2W-1  "out[j]"   reduced slice j, pushed by rank j (LL) or multicast by
+                                    //                               the switch (NVLS)
+                                    // Always all-SENTINEL outside a running collective: a consumer recognises arrived data
+                                    // word by word as "not the sentinel" (no flag, no fence, no barrier) and puts the
+                                    // sentinel back after reading.
+  unsigned long long llflag_off;    // 8 x u32: llflag[r] = op counter of the latest LL collective rank r has STARTED
+                                    // (flow control: nobody writes a parity's buffers before their owner has left the
+                                    // collective that last used them)
   unsigned long long* trace;        // optional (b2_comm_trace): per-CTA globaltimer stamps of the LAST collective,
                                     // 8 slots per CTA (see include/b200ddp.h)
 };

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const unsigned long long Ls = (V + W - 1) / W;
   const unsigned long long g = gridDim.x, b = blockIdx.x;
   const unsigned long long reduced = stage + static_cast<unsigned long long>(W) * c.slice_cap;  // P2P only
-  const unsigned long long nvls_out = (seq0 & 1u) ? c.nvls_out_off[1] : c.nvls_out_off[0];        // NVLS only
+  const unsigned long long nvls_out = ((seq0 & 1u) ? c.ll_off[1] : c.ll_off[0]) + static_cast<unsigned long long>(W) * c.slice_cap;  // NVLS only: "out" regions
   uint8_t* const mine = c.peer[0];
   const int tid = threadIdx.x;
   // chunks this CTA really has: cell (k, b) starts at (k*g + b)*cell, empty from the first k with start >= Ls on
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if constexpr (ALG == kNvls) {
         constexpr int UM = MODE == B2_F32 ? 4 : 8;  // 128 B of switch-side reductions in flight per thread
         const uint8_t* const mc_in = c.mc + stage;   // every rank's staged contribution, summed by the switch on load
-        uint8_t* const mc_out = c.mc + nvls_out;     // every rank's output buffer, written by the switch on store
+        uint8_t* const mc_out = c.mc + nvls_out + c.rank * c.slice_cap;  // out[me] on every rank, written by the switch on store
         for (unsigned long long v0 = lo + t; v0 < hi; v0 += static_cast<unsigned long long>(kBD) * UM) {
           Wire<MODE> q[UM];
 #pragma unroll
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
           for (int u = 0; u < UM; ++u) {
             const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kBD;
-            if (v < hi && base + v < V) mm_st_wire<MODE>(mc_out + (base + v) * WVB, wire_no_sentinel<MODE>(q[u]));
+            if (v < hi && base + v < V) mm_st_wire<MODE>(mc_out + v * WVB, wire_no_sentinel<MODE>(q[u]));
           }
         }
       } else {
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             pend[u][jj] = false;
             if (v < hi && gv < V) {
               if constexpr (ALG == kNvls)
-                w[u][jj] = wire_poll<MODE>(mine + nvls_out + gv * WVB, &pend[u][jj]);  // the switch multicasts every slice here
+                w[u][jj] = wire_poll<MODE>(mine + nvls_out + j * c.slice_cap + v * WVB, &pend[u][jj]);  // out[j]: multicast by the switch
               else
                 w[u][jj] = ld_wire<MODE>(c.peer[jj] + reduced + v * WVB);  // rank j's reduced slice, over NVLink
             }
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (!pend[u][jj]) continue;
               int j = c.rank + jj;
               if (j >= W) j -= W;
-              const uint8_t* p = mine + nvls_out + (j * Ls + v) * WVB;
+              const uint8_t* p = mine + nvls_out + j * c.slice_cap + v * WVB;
               unsigned long long t0 = 0;
               unsigned spins = 0;
               bool pending = true;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             const unsigned long long gv = j * Ls + v;
             if (v < hi && gv < V) {
               store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
-              if constexpr (ALG == kNvls) wire_reset<MODE>(mine + nvls_out + gv * WVB);  // back to "not written yet"
+              if constexpr (ALG == kNvls) wire_reset<MODE>(mine + nvls_out + j * c.slice_cap + v * WVB);  // back to "not written yet"
             }
           }
         }

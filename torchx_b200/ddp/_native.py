@@ -38,6 +38,7 @@ B2_ALGO_ONESHOT = 1
 B2_ALGO_TWOSHOT = 2
 B2_ALGO_TWOSHOT_PIPE = 3
 B2_ALGO_NVLS = 4
+B2_ALGO_TWOSHOT_LL = 5
 
 B2_CAP_VMM = 1
 B2_CAP_MULTICAST = 2

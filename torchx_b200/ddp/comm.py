@@ -21,7 +21,7 @@ _MODE_FOR = {
     ("bf16", "bf16"): N.B2_BF16,
 }
 ALGOS = {"auto": N.B2_ALGO_AUTO, "oneshot": N.B2_ALGO_ONESHOT, "twoshot": N.B2_ALGO_TWOSHOT, "twoshot_pipe": N.B2_ALGO_TWOSHOT_PIPE,
-         "nvls": N.B2_ALGO_NVLS}
+         "nvls": N.B2_ALGO_NVLS, "twoshot_ll": N.B2_ALGO_TWOSHOT_LL}
 
 
 def mode_for(tensor: torch.Tensor, wire: str = "bf16") -> int:

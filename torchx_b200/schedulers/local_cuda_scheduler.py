@@ -531,6 +531,11 @@ class LocalCudaScheduler(LocalScheduler):
         })
         if g.devices[local_rank] >= 0:
             env["B2_DEVICE"] = str(g.devices[local_rank])
+        if ENV_CUDA_VISIBLE_DEVICES in g.env and g.group_world_size > 1:
+            # several "nodes" on one box, each with its own CUDA_VISIBLE_DEVICES: a peer's GPU is not visible to this process,
+            # so the VMM import (cuMemSetAccess on an invisible device) and a multicast team cannot be set up; CUDA IPC can
+            # open an invisible peer's memory - stay on that arena backend
+            env.setdefault("B2_VMM", "0")
         if req.stage_mb:
             env["B2_STAGE_MB"] = str(req.stage_mb)
         if "OMP_NUM_THREADS" not in env and "OMP_NUM_THREADS" not in os.environ:
