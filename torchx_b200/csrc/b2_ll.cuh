@@ -9,7 +9,7 @@
 //   1  push-scatter : read my bucket once, cast+scale, STORE slice j into rank j's recv[me]              (NVLink egress)
 //   2  reduce+push  : poll MY recv[0..W-1] for my slice until every 32-bit word has arrived, fp32 accumulate in rank
 //                     order, round once, STORE the reduced slice into out[me] of EVERY rank               (NVLink egress)
-//   3  widen        : poll MY out[0..W-1], widen, write my bucket
+//   3  widen        : poll MY out[0..W-1], widen, write my bucket          (local only; interleaved with phase 2, one trip behind)
 //
 // "Arrived" = the word no longer holds the SENTINEL the buffers are kept filled with (kSentinel: a NaN pattern that the
 // producers canonicalise away, so data never contains it).  Each 4-byte word is validated on its own, so no assumption
@@ -112,73 +112,80 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
   if (threadIdx.x == 0) trace_stamp(c, 2);
 
-  // ---- phase 2: reduce my slice as its contributions arrive, push the result to everyone -------
+  // ---- phases 2 and 3, interleaved: in trip i a thread reduces + pushes its vecs of trip i (NVLink egress) and widens
+  // the vecs of trip i-1 (local L2/HBM only), whose slices the peers pushed one trip ago - so the final local pass hides
+  // behind the pushes instead of following them (for a 256 MiB bucket it is ~100 us of HBM traffic).  No cycle: widening
+  // trip k needs the peers' pushes of trip k, which they issue before they widen trip k-1.
   {
     const unsigned long long base = c.rank * Ls;
-    for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
-      Wire<MODE> w[U][W];
-      bool pend[U][W];
+    const unsigned long long step = stride * U;
+    for (unsigned long long v0 = first;; v0 += step) {
+      const bool do2 = v0 < Ls;
+      const bool do3 = v0 >= step + first && v0 - step < Ls;
+      if (!do2 && !do3) break;
+      if (do2) {  // ---- phase 2: reduce my slice as its contributions arrive, push the result to everyone
+        Wire<MODE> w[U][W];
+        bool pend[U][W];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const unsigned long long v = v0 + u * stride;
-#pragma unroll
-        for (int r = 0; r < W; ++r) {
-          pend[u][r] = false;
-          if (v < Ls && base + v < V) w[u][r] = wire_poll<MODE>(mine + base_ll + r * c.slice_cap + v * WVB, &pend[u][r]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const unsigned long long v = v0 + u * stride;
-        if (v < Ls && base + v < V) {
+        for (int u = 0; u < U; ++u) {
+          const unsigned long long v = v0 + u * stride;
 #pragma unroll
           for (int r = 0; r < W; ++r) {
-            const uint8_t* p = mine + base_ll + r * c.slice_cap + v * WVB;
-            if (pend[u][r]) ll::wait_vec<MODE>(c, p, w[u][r], true);
-            wire_reset<MODE>(const_cast<uint8_t*>(p));  // back to "not written yet" for the collective after next
+            pend[u][r] = false;
+            if (v < Ls && base + v < V) w[u][r] = wire_poll<MODE>(mine + base_ll + r * c.slice_cap + v * WVB, &pend[u][r]);
           }
-          F8 s = widen<MODE>(w[u][0]);
+        }
 #pragma unroll
-          for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));  // rank order, fp32
-          const Wire<MODE> q = wire_no_sentinel<MODE>(finalize<MODE>(s));
+        for (int u = 0; u < U; ++u) {
+          const unsigned long long v = v0 + u * stride;
+          if (v < Ls && base + v < V) {
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) st_wire<MODE>(c.peer[jj] + my_out + v * WVB, q);
+            for (int r = 0; r < W; ++r) {
+              const uint8_t* p = mine + base_ll + r * c.slice_cap + v * WVB;
+              if (pend[u][r]) ll::wait_vec<MODE>(c, p, w[u][r], true);
+              wire_reset<MODE>(const_cast<uint8_t*>(p));  // back to "not written yet" for the collective after next
+            }
+            F8 s = widen<MODE>(w[u][0]);
+#pragma unroll
+            for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));  // rank order, fp32
+            const Wire<MODE> q = wire_no_sentinel<MODE>(finalize<MODE>(s));
+#pragma unroll
+            for (int jj = 0; jj < W; ++jj) st_wire<MODE>(c.peer[jj] + my_out + v * WVB, q);
+          }
         }
       }
-    }
-  }
-  if (threadIdx.x == 0) trace_stamp(c, 3);
-
-  // ---- phase 3: widen every slice as it arrives --------------------------------------------------
-  for (unsigned long long v0 = first; v0 < Ls; v0 += stride * U) {
-    Wire<MODE> w[U][W];
-    bool pend[U][W];
+      if (do3) {  // ---- phase 3: widen every slice of the previous trip as it arrives
+        const unsigned long long p0 = v0 - step;
+        Wire<MODE> w[U][W];
+        bool pend[U][W];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned long long v = v0 + u * stride;
+        for (int u = 0; u < U; ++u) {
+          const unsigned long long v = p0 + u * stride;
 #pragma unroll
-      for (int jj = 0; jj < W; ++jj) {
-        int j = c.rank + jj;
-        if (j >= W) j -= W;
-        const unsigned long long gv = j * Ls + v;
-        pend[u][jj] = false;
-        if (v < Ls && gv < V)
-          w[u][jj] = wire_poll<MODE>(mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB, &pend[u][jj]);
-      }
-    }
+          for (int jj = 0; jj < W; ++jj) {
+            int j = c.rank + jj;
+            if (j >= W) j -= W;
+            const unsigned long long gv = j * Ls + v;
+            pend[u][jj] = false;
+            if (v < Ls && gv < V)
+              w[u][jj] = wire_poll<MODE>(mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB, &pend[u][jj]);
+          }
+        }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const unsigned long long v = v0 + u * stride;
+        for (int u = 0; u < U; ++u) {
+          const unsigned long long v = p0 + u * stride;
 #pragma unroll
-      for (int jj = 0; jj < W; ++jj) {
-        int j = c.rank + jj;
-        if (j >= W) j -= W;
-        const unsigned long long gv = j * Ls + v;
-        if (v < Ls && gv < V) {
-          uint8_t* p = mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB;
-          if (pend[u][jj]) ll::wait_vec<MODE>(c, p, w[u][jj], true);
-          store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
-          wire_reset<MODE>(p);
+          for (int jj = 0; jj < W; ++jj) {
+            int j = c.rank + jj;
+            if (j >= W) j -= W;
+            const unsigned long long gv = j * Ls + v;
+            if (v < Ls && gv < V) {
+              uint8_t* p = mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB;
+              if (pend[u][jj]) ll::wait_vec<MODE>(c, p, w[u][jj], true);
+              store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
+              wire_reset<MODE>(p);
+            }
+          }
         }
       }
     }
