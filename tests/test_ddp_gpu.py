@@ -205,17 +205,20 @@ def test_comm_hook_on_stock_ddp_world1():
         dist.destroy_process_group()
 
 
-def _convnet(seed):
+def _ragged_mlp(seed):
     torch.manual_seed(seed)
-    # channels_last conv weights (gradient views get channels_last strides) + sizes that are not multiples of 8
-    net = nn.Sequential(nn.Conv2d(3, 5, 3, bias=True), nn.ReLU(), nn.Conv2d(5, 7, 3), nn.ReLU(), nn.Flatten(), nn.Linear(7 * 4 * 4, 11))
-    return net.cuda().to(memory_format=torch.channels_last)
+    # 37- and 13-wide layers: parameter sizes that are not multiples of 8, so later parameters start at bucket offsets that
+    # are not vec-aligned (segment-straddling vecs in the zero-copy bucket fill).  No cuDNN here on purpose: an in-process
+    # world cannot survive a first-use cudaMalloc / device-wide sync while a peer's kernel spins (the convnet / channels_last
+    # variant runs one process per rank in tests/test_hook_multirank_gpu.py).
+    return nn.Sequential(nn.Linear(64, 256), nn.ReLU(), nn.Linear(256, 37), nn.ReLU(), nn.Linear(37, 13)).cuda()
 
 
 @pytest.mark.parametrize("zero_copy", [True, False])
 def test_zero_copy_bucket_fill_equals_copy_in(zero_copy):
-    """The kernel gathers the gradients straight from the per-parameter tensors (pointer table) - same bits as copying
-    them into the bucket first; channels_last weights, ragged sizes, segment-straddling vecs."""
+    """The kernel gathers the gradients straight from the per-parameter tensors (segment table in the kernel parameters) -
+    same bits as copying them into the bucket first; ragged sizes, segment-straddling vecs, gradients that already ARE the
+    bucket views (zero_grad(set_to_none=False))."""
     from torchx_b200.ddp import Communicator, DistributedDataParallel
 
     W = 2
@@ -227,26 +230,20 @@ def test_zero_copy_bucket_fill_equals_copy_in(zero_copy):
             comms[r].set_timeout(20.0)
             comms[r].set_max_ctas(4)
             with torch.cuda.stream(streams[r]):
-                ddps.append(DistributedDataParallel(_convnet(0), comms[r], bucket_cap_mb=0.002, first_bucket_mb=0.0005, zero_copy=zero_copy))
+                ddps.append(DistributedDataParallel(_ragged_mlp(0), comms[r], bucket_cap_mb=0.02, first_bucket_mb=0.002, zero_copy=zero_copy))
         torch.cuda.synchronize()
         assert len(ddps[0].buckets) >= 2
         for step in range(3):
-            xs = [torch.randn(4, 3, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(7 * step + r)).contiguous(memory_format=torch.channels_last) for r in range(W)]
+            xs = [torch.randn(8, 64, device="cuda", generator=torch.Generator("cuda").manual_seed(7 * step + r)) for r in range(W)]
             local = []
             for r in range(W):
-                twin = _convnet(0)
+                twin = _ragged_mlp(0)
                 twin(xs[r]).square().mean().backward()
                 local.append(_flat_grads(twin))
-            def one_step(r, step=step, xs=xs):
-                # one host thread per rank, like the real topology: a host-side sync in one rank's step (first-use cuDNN
-                # workspace / allocator growth = cudaMalloc = device-wide sync) must not keep the other rank from launching
-                # the kernels this rank's collectives are spinning on
+            for r in range(W):
                 with torch.cuda.stream(streams[r]):
                     ddps[r].zero_grad(set_to_none=(step != 1))  # step 1: grads stay bucket views and accumulate in place
                     ddps[r](xs[r]).square().mean().backward()
-                    streams[r].synchronize()
-
-            _run_ranks(W, one_step)
             torch.cuda.synchronize()
             for c in comms:
                 c.check()

@@ -45,6 +45,11 @@ def _run(world, devices, backend, tmp_path):
         assert_bits_equal(got[r]["mini"], want, f"mini-DDP, rank {r}")
         gathered, copied = got[r]["mini_gathered"]
         assert gathered > 0 and copied == 0, (gathered, copied)  # every bucket was read in place, none copied in
+    want_conv = oracle.allreduce(oracle.B2O_F32_WIRE_BF16, [g["conv_local"] for g in got], 1.0 / world)
+    for r in range(world):
+        assert_bits_equal(got[r]["conv_zero_copy"], want_conv, f"convnet, zero-copy bucket fill, rank {r}")
+        assert_bits_equal(got[r]["conv_copy_in"], want_conv, f"convnet, copy-in, rank {r}")
+        assert got[r]["conv_zero_copy_counts"][0] > 0 and got[r]["conv_copy_in_counts"][0] == 0
     return got
 
 

@@ -73,6 +73,28 @@ def main() -> None:
     res["mini"] = flat_grads(m2)
     res["mini_gathered"] = np.array([d2.gathered_buckets, d2.copied_in_buckets])
 
+    # channels_last conv weights (gradient views with channels_last strides), ragged sizes, tiny buckets: zero-copy bucket fill
+    # (kernel reads the gradients in place) against the copy-in path, bit for bit
+    def convnet():
+        torch.manual_seed(0)
+        net = nn.Sequential(nn.Conv2d(3, 5, 3, bias=True), nn.ReLU(), nn.Conv2d(5, 7, 3), nn.ReLU(), nn.Flatten(), nn.Linear(7 * 4 * 4, 11))
+        return net.cuda().to(memory_format=torch.channels_last)
+
+    xc = torch.randn(4, 3, 8, 8, device="cuda", generator=torch.Generator("cuda").manual_seed(200 + a.rank)).contiguous(memory_format=torch.channels_last)
+    tw = convnet()
+    tw(xc).square().mean().backward()
+    res["conv_local"] = flat_grads(tw)
+    for tag, zc in (("conv_zero_copy", True), ("conv_copy_in", False)):
+        m4 = convnet()
+        d4 = DistributedDataParallel(m4, comm, bucket_cap_mb=0.002, first_bucket_mb=0.0005, zero_copy=zc)
+        for step in range(3):
+            d4.zero_grad(set_to_none=(step != 1))
+            d4(xc).square().mean().backward()
+        torch.cuda.synchronize()
+        comm.check()
+        res[tag] = flat_grads(m4)
+        res[tag + "_counts"] = np.array([d4.gathered_buckets, d4.copied_in_buckets])
+
     if a.backend == "nccl":  # the reference's own hook over NCCL: at W = 2 one fp32 add, one rounding => same bits as ours
         m3 = mlp(0)
         d3 = TorchDDP(m3, device_ids=[a.device], bucket_cap_mb=0.05)
