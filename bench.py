@@ -480,14 +480,19 @@ class Trainer:
             res["nvls"] = nvls_stats
             if nvls_stats["worse_than_one_bf16_ulp"]:
                 res["bit_exact"] = False
-        if W == 2:
-            res["vs_nccl_bf16_w2_bit_equal"] = self.nccl_bit_equal_w2()
+        res["vs_nccl_bf16_bit_equal"] = self.nccl_bit_equal(sizes)
+        if W == 2 and isinstance(res["vs_nccl_bf16_bit_equal"], dict):
+            res["vs_nccl_bf16_w2_bit_equal"] = all(res["vs_nccl_bf16_bit_equal"].values())
+        res["note"] = ("bit_exact: every rank-order algorithm (one-shot, two-shot, LL two-shot, pipelined two-shot, and whatever AUTO picked "
+                       "among them) equals the CPU oracle bit for bit.  nvls: the NVSwitch's own arithmetic - within one bf16 ulp of the exact "
+                       "sum, bit-identical to NCCL's NVLS allreduce (profiles/r02_nvls_rounding.md).  vs_nccl_bf16_bit_equal: AUTO's result "
+                       "against the reference hook sequence over NCCL per bucket size - must hold at W=2 (one add); at W>2 it holds "
+                       "where both sides take the NVLS path and cannot hold where NCCL uses its ring/tree order with bf16 partial sums.")
         return res
 
-    def nccl_bit_equal_w2(self):
-        """W = 2 only: the reference hook sequence over NCCL (cast, div, ncclAllReduce, copy) is one fp32 add and one rounding,
-        so it must give the same BITS as the fused kernel.  torch.distributed is initialised here, after every timed region,
-        for this comparison alone."""
+    def nccl_bit_equal(self, sizes_mib):
+        """AUTO's result against the reference hook sequence over NCCL (cast, div, ncclAllReduce, copy), bit for bit, per bucket
+        size.  torch.distributed is initialised here, after every timed region, for this comparison alone."""
         torch = self.torch
         import torch.distributed as dist
 
@@ -496,8 +501,9 @@ class Trainer:
             if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
                 os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", rank=self.rank, world_size=self.world, device_id=self.device)
-            ok = True
-            for n in (4099, 1 << 20, 6_563_840):
+            out = {}
+            for mib in sizes_mib:
+                n = int(mib * (1 << 20) / 4)
                 g = torch.Generator(device=self.device).manual_seed(1234 + self.rank)
                 buf = torch.randn(n, device=self.device, generator=g)
                 ours = buf.clone()
@@ -506,9 +512,12 @@ class Trainer:
                 dist.all_reduce(c)
                 ref = buf.clone().copy_(c)
                 torch.cuda.synchronize()
-                ok = ok and bool(torch.equal(ours, ref))
+                eq = torch.tensor([int(torch.equal(ours, ref))], device=self.device)
+                dist.all_reduce(eq, op=dist.ReduceOp.MIN)
+                out[f"{mib}:{self.comm.last_algo}"] = bool(eq.item())
+                del buf, ours, c, ref
             dist.destroy_process_group()
-            return ok
+            return out
         except Exception as e:  # noqa: BLE001 - a missing NCCL must not take the bench line down
             return f"unavailable: {type(e).__name__}: {e}"[:200]
 

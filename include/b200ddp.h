@@ -128,7 +128,8 @@ int b2_comm_set_max_ctas(b2_comm_t* comm, int max_ctas);
  *   "pipe_min_bytes"     pipelined two-shot from this many wire bytes   (env B2_PIPE_MIN_BYTES)
  *   "nvls_min_bytes"     NVLS from this many wire bytes                 (env B2_NVLS_MIN_BYTES)
  *   "nvls_min_world"     NVLS from this world size                      (env B2_NVLS_MIN_WORLD)
- *   "ll_min_bytes"       barrier-free LL two-shot from this many wire bytes (env B2_LL_MIN_BYTES)
+ *   "ll_min_bytes"       barrier-free LL two-shot from this many wire bytes (env B2_LL_MIN_BYTES) ...
+ *   "ll_max_bytes"       ... up to (excluding) this many                (env B2_LL_MAX_BYTES)
  *   "pipe_chunk_bytes"   target wire bytes per pipeline chunk           (env B2_PIPE_CHUNK_KB, in KiB)
  *   "max_ctas"           same as b2_comm_set_max_ctas
  */

@@ -148,7 +148,8 @@ struct b2_comm {
   size_t pipe_min_wire_bytes = 0;     // AUTO: the pipelined kernels from this many wire bytes
   size_t nvls_min_wire_bytes = 0;     // AUTO: NVLS (when available and the mode allows it) from this many wire bytes
   int nvls_min_world = 4;             // AUTO: NVLS only pays once (1 + 1/W) < 2 (W-1)/W, i.e. W >= 4
-  size_t ll_min_wire_bytes = 0;       // AUTO: the barrier-free LL two-shot from this many wire bytes
+  size_t ll_min_wire_bytes = 0;       // AUTO: the barrier-free LL two-shot from this many wire bytes (above the one-shot range) ...
+  size_t ll_max_wire_bytes = 0;       // ... up to (excluding) this many
   size_t pipe_chunk_bytes = 0;        // target wire bytes of one pipeline chunk (per rank)
   uint64_t launches = 0;
   int last_algo = 0;                  // B2_ALGO_* of the most recent allreduce launch (what AUTO picked)
@@ -206,12 +207,20 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   layout(c, world, stage_bytes);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
   c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
-  // Provisional AUTO thresholds (8xB200, profiles/r02_sweep_w8.md): the single-pass two-shot kernel wins up to ~256 MiB of
-  // wire data; the NVLS path only overtakes it for the largest messages.
+  // AUTO thresholds from the measured sweeps (profiles/r02_sweep_w8.md, r02_pipeline_and_ll_w2.md), in wire bytes:
+  //   one-shot            up to default_oneshot_max(world)
+  //   LL two-shot         from there to 8 MiB at W >= 3 (2-16 MiB fp32 buckets at W=8: 5-9 % ahead of the single-pass kernel;
+  //                       at W=2 one-shot covers that range and LL loses above it: off)
+  //   single-pass two-shot  above that (the DDP 25 MiB buckets: equal in isolation, and the kernel with no extra local
+  //                       traffic when backward competes for HBM inside the training step)
+  //   NVLS                from 64 MiB at W = 8 (128 MiB-1 GiB fp32: 245 / 336 / 1281 us against 268 / 397 / 1542 us two-shot and
+  //                       357 / 394 / 1330 us ncclAllReduce); the switch's arithmetic, bit-identical to NCCL's NVLS
+  //   pipelined two-shot  never (explicit choice only)
   c->pipe_min_wire_bytes = env_size("B2_PIPE_MIN_BYTES", ~static_cast<size_t>(0));
-  c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 256u << 20);
-  c->nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 4));
-  c->ll_min_wire_bytes = env_size("B2_LL_MIN_BYTES", ~static_cast<size_t>(0));
+  c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 64u << 20);
+  c->nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 8));
+  c->ll_min_wire_bytes = env_size("B2_LL_MIN_BYTES", world >= 3 ? 0 : ~static_cast<size_t>(0));
+  c->ll_max_wire_bytes = env_size("B2_LL_MAX_BYTES", 8u << 20);
   c->pipe_chunk_bytes = env_size("B2_PIPE_CHUNK_KB", 2048) << 10;
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->counters, 256));
@@ -925,6 +934,7 @@ int b2_comm_set_param(b2_comm_t* c, const char* name, long long value) {
   else if (k == "nvls_min_bytes") c->nvls_min_wire_bytes = static_cast<size_t>(value);
   else if (k == "nvls_min_world") c->nvls_min_world = static_cast<int>(value);
   else if (k == "ll_min_bytes") c->ll_min_wire_bytes = static_cast<size_t>(value);
+  else if (k == "ll_max_bytes") c->ll_max_wire_bytes = static_cast<size_t>(value);
   else if (k == "pipe_chunk_bytes") c->pipe_chunk_bytes = static_cast<size_t>(value);
   else if (k == "max_ctas") c->max_ctas = static_cast<int>(value);
   else return fail(B2_EINVAL, "b2_comm_set_param: unknown parameter '%s'", name);
@@ -997,7 +1007,7 @@ static int allreduce_impl(b2_comm_t* c, Src& src, void* buf, size_t n_elems, int
         kind = B2_ALGO_NVLS;
       else if (wire_left <= c->oneshot_max_wire_bytes && V_left <= cap_vecs)
         kind = B2_ALGO_ONESHOT;
-      else if (wire_left >= c->ll_min_wire_bytes)
+      else if (wire_left >= c->ll_min_wire_bytes && wire_left < c->ll_max_wire_bytes)
         kind = B2_ALGO_TWOSHOT_LL;
       else if (wire_left >= c->pipe_min_wire_bytes)
         kind = B2_ALGO_TWOSHOT_PIPE;
