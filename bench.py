@@ -635,7 +635,9 @@ def main():
             line["roofline"] = {
                 "bound": "hbm", "achieved": round(hbm_gbs, 1), "peak": peak, "unit": "GB/s", "frac": round(hbm_gbs / peak, 4), "traffic": None,
                 "peak_source": peak_src,
-                "note": "8 B per gradient element (read fp32 once, write fp32 once), timed with CUDA events on the comm stream while backward runs beside it",
+                "note": "8 B per gradient element (read fp32 once, write fp32 once), timed with CUDA events on the comm stream while backward runs beside it; "
+                        "with gathered_buckets > 0 this one launch also IS the bucket fill (it reads the per-parameter gradient tensors through the "
+                        "segment table): the Reducer-style copy-in pass of round 1 - another 8 B per element and one multi-tensor launch per bucket - no longer exists",
                 **common}
             tpath = os.path.join(ROOT, "profiles", "r01_local_pass_traffic.json")
             if os.path.exists(tpath):
