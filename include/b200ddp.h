@@ -123,6 +123,14 @@ int b2_comm_set_timeout_ms(b2_comm_t* comm, int timeout_ms);
 int b2_comm_set_max_ctas(b2_comm_t* comm, int max_ctas);
 
 /*
+ * What B2_ALGO_AUTO resolves to for a message of `n_elems` elements in `mode` on `world` ranks with the library's default
+ * thresholds (and the B2_* environment overrides); `has_multicast` = the communicator would have B2_CAP_MULTICAST.  Pure
+ * function, no GPU needed: lets a caller (and the CPU test-suite) see the policy table of DESIGN.md 2.6.  Messages larger
+ * than a staging buffer are cut into several launches, each resolved on its own size.  world == 1: B2_ALGO_AUTO (local pass).
+ */
+int b2_auto_algo(int world, int mode, size_t n_elems, int has_multicast);
+
+/*
  * Tuning knobs of the AUTO algorithm choice and of the pipelined kernels; must be set identically on every rank.
  *   "oneshot_max_bytes"  one-shot up to this many wire bytes           (env B2_ONESHOT_MAX_BYTES)
  *   "pipe_min_bytes"     pipelined two-shot from this many wire bytes   (env B2_PIPE_MIN_BYTES)

@@ -176,6 +176,32 @@ size_t default_oneshot_max(int world) {
   return 512u << 10;
 }
 
+// What B2_ALGO_AUTO resolves to for one launch.  Pure: the same inputs give the same answer on every rank.
+struct AutoPolicy {
+  size_t oneshot_max, ll_min, ll_max, pipe_min, nvls_min;
+  int nvls_min_world;
+};
+
+AutoPolicy default_policy(int world) {
+  AutoPolicy p;
+  p.oneshot_max = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
+  p.pipe_min = env_size("B2_PIPE_MIN_BYTES", ~static_cast<size_t>(0));
+  p.nvls_min = env_size("B2_NVLS_MIN_BYTES", 64u << 20);
+  p.nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 8));
+  p.ll_min = env_size("B2_LL_MIN_BYTES", world >= 3 ? 0 : ~static_cast<size_t>(0));
+  p.ll_max = env_size("B2_LL_MAX_BYTES", 8u << 20);
+  return p;
+}
+
+int auto_algo(const AutoPolicy& p, int world, int mode, size_t wire_bytes, bool multicast, bool fits_oneshot) {
+  // fp32-wire NVLS would let the switch pick the fp32 summation order; AUTO keeps that mode on the rank-order kernels
+  if (multicast && mode != B2_F32 && world >= p.nvls_min_world && wire_bytes >= p.nvls_min) return B2_ALGO_NVLS;
+  if (wire_bytes <= p.oneshot_max && fits_oneshot) return B2_ALGO_ONESHOT;
+  if (wire_bytes >= p.ll_min && wire_bytes < p.ll_max) return B2_ALGO_TWOSHOT_LL;
+  if (wire_bytes >= p.pipe_min) return B2_ALGO_TWOSHOT_PIPE;
+  return B2_ALGO_TWOSHOT;
+}
+
 // Arena layout for a given world size; fills d.*_off / d.slice_cap and arena_bytes (before backend rounding).
 void layout(b2_comm* c, int world, size_t stage_bytes) {
   size_t cap = stage_bytes / (world + 1);
@@ -206,7 +232,6 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   c->d.timeout_ns = env_size("B2_TIMEOUT_MS", kDefaultTimeoutNs / 1000000ull) * 1000000ull;
   layout(c, world, stage_bytes);
   c->max_ctas = static_cast<int>(env_size("B2_MAX_CTAS", 0));
-  c->oneshot_max_wire_bytes = env_size("B2_ONESHOT_MAX_BYTES", default_oneshot_max(world));
   // AUTO thresholds from the measured sweeps (profiles/r02_sweep_w8.md, r02_pipeline_and_ll_w2.md), in wire bytes:
   //   one-shot            up to default_oneshot_max(world)
   //   LL two-shot         from there to 8 MiB at W >= 3 (2-16 MiB fp32 buckets at W=8: 5-9 % ahead of the single-pass kernel;
@@ -216,11 +241,13 @@ int init_rank(b2_comm* c, int rank, int world, int device, size_t stage_bytes) {
   //   NVLS                from 64 MiB at W = 8 (128 MiB-1 GiB fp32: 245 / 336 / 1281 us against 268 / 397 / 1542 us two-shot and
   //                       357 / 394 / 1330 us ncclAllReduce); the switch's arithmetic, bit-identical to NCCL's NVLS
   //   pipelined two-shot  never (explicit choice only)
-  c->pipe_min_wire_bytes = env_size("B2_PIPE_MIN_BYTES", ~static_cast<size_t>(0));
-  c->nvls_min_wire_bytes = env_size("B2_NVLS_MIN_BYTES", 64u << 20);
-  c->nvls_min_world = static_cast<int>(env_size("B2_NVLS_MIN_WORLD", 8));
-  c->ll_min_wire_bytes = env_size("B2_LL_MIN_BYTES", world >= 3 ? 0 : ~static_cast<size_t>(0));
-  c->ll_max_wire_bytes = env_size("B2_LL_MAX_BYTES", 8u << 20);
+  const AutoPolicy pol = default_policy(world);
+  c->oneshot_max_wire_bytes = pol.oneshot_max;
+  c->pipe_min_wire_bytes = pol.pipe_min;
+  c->nvls_min_wire_bytes = pol.nvls_min;
+  c->nvls_min_world = pol.nvls_min_world;
+  c->ll_min_wire_bytes = pol.ll_min;
+  c->ll_max_wire_bytes = pol.ll_max;
   c->pipe_chunk_bytes = env_size("B2_PIPE_CHUNK_KB", 2048) << 10;
   B2_CUDA(cudaSetDevice(device));
   B2_CUDA(cudaMalloc(&c->counters, 256));
@@ -953,6 +980,14 @@ uint64_t b2_comm_launch_count(const b2_comm_t* c) { return c ? c->launches : 0; 
 
 int b2_comm_last_algo(const b2_comm_t* c) { return c ? c->last_algo : B2_EINVAL; }
 
+int b2_auto_algo(int world, int mode, size_t n_elems, int has_multicast) {
+  if (world < 1 || world > B2_MAX_WORLD || (mode != B2_F32_WIRE_BF16 && mode != B2_F32 && mode != B2_BF16))
+    return fail(B2_EINVAL, "b2_auto_algo: bad arguments (world=%d mode=%d)", world, mode);
+  if (world == 1 || n_elems == 0) return B2_ALGO_AUTO;  // no collective: the local pass
+  const size_t wire = (n_elems + 7) / 8 * wire_vec_bytes(mode);
+  return auto_algo(default_policy(world), world, mode, wire, has_multicast != 0, true);
+}
+
 int b2_comm_trace(b2_comm_t* c, int enable, uint64_t* out, int max_ctas) {
   if (!c) return fail(B2_EINVAL, "null communicator");
   DeviceGuard g(c->device);
@@ -1002,17 +1037,9 @@ static int allreduce_impl(b2_comm_t* c, Src& src, void* buf, size_t n_elems, int
     const size_t wire_left = V_left * wvb;
     int kind;
     if (algo == B2_ALGO_AUTO) {
-      // fp32-wire NVLS would let the switch pick the fp32 summation order; AUTO keeps that mode on the rank-order kernels
-      if (c->d.mc != nullptr && mode != B2_F32 && W >= c->nvls_min_world && wire_left >= c->nvls_min_wire_bytes)
-        kind = B2_ALGO_NVLS;
-      else if (wire_left <= c->oneshot_max_wire_bytes && V_left <= cap_vecs)
-        kind = B2_ALGO_ONESHOT;
-      else if (wire_left >= c->ll_min_wire_bytes && wire_left < c->ll_max_wire_bytes)
-        kind = B2_ALGO_TWOSHOT_LL;
-      else if (wire_left >= c->pipe_min_wire_bytes)
-        kind = B2_ALGO_TWOSHOT_PIPE;
-      else
-        kind = B2_ALGO_TWOSHOT;
+      AutoPolicy pol{c->oneshot_max_wire_bytes, c->ll_min_wire_bytes, c->ll_max_wire_bytes, c->pipe_min_wire_bytes,
+                     c->nvls_min_wire_bytes, c->nvls_min_world};
+      kind = auto_algo(pol, W, mode, wire_left, c->d.mc != nullptr, V_left <= cap_vecs);
     } else {
       kind = algo;
     }

@@ -71,6 +71,7 @@ SYMBOLS = [
     "b2_comm_status",
     "b2_comm_launch_count",
     "b2_comm_last_algo",
+    "b2_auto_algo",
     "b2_comm_trace",
     "b2_allreduce",
     "b2_allreduce_gather",
@@ -145,6 +146,8 @@ def lib() -> ctypes.CDLL:
     L.b2_comm_set_max_ctas.argtypes = [vp, i]
     L.b2_comm_set_param.restype = i
     L.b2_comm_set_param.argtypes = [vp, ctypes.c_char_p, ctypes.c_longlong]
+    L.b2_auto_algo.restype = i
+    L.b2_auto_algo.argtypes = [i, i, sz, i]
     L.b2_comm_launch_count.restype = u64
     L.b2_comm_launch_count.argtypes = [vp]
     L.b2_comm_trace.restype = i
