@@ -452,20 +452,35 @@ __device__ __forceinline__ bool buf_aligned(const void* buf) {
 }
 
 // One input vec (elements [e, e + 8) of this launch) from wherever `src` says the input lives.
+// The segment a thread found last: consecutive vecs of one thread usually fall into the same parameter, so the binary
+// search over the table (dependent constant-bank loads in front of the data load) is skipped most of the time.
+struct SegHint {
+  int s = 0;
+  unsigned long long sb = 1, se = 0;  // empty range: the first lookup searches
+};
+
 template <int MODE>
-__device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned long long e, unsigned long long n,
-                                       bool aligned) {
+__device__ __forceinline__ F8 load_src(const Src& src, SegHint& hint, const void* buf, unsigned long long e,
+                                       unsigned long long n, bool aligned) {
   if (src.nseg == 0) return load_in<MODE>(buf, e, n, aligned);
   using Elem = typename std::conditional<MODE == B2_BF16, uint16_t, float>::type;
   const unsigned long long ge = e + src.off;  // bucket coordinates
-  int lo = 0, hi = src.nseg;                  // begin[lo] <= ge < begin[hi]
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (ge >= src.begin[mid]) lo = mid;
-    else hi = mid;
+  int s = hint.s;
+  unsigned long long sb = hint.sb, se = hint.se;
+  if (ge < sb || ge >= se) {                  // not in the segment this thread looked at last: binary search
+    int lo = 0, hi = src.nseg;                // begin[lo] <= ge < begin[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (ge >= src.begin[mid]) lo = mid;
+      else hi = mid;
+    }
+    s = lo;
+    sb = src.begin[s];
+    se = src.begin[s + 1];
+    hint.s = s;
+    hint.sb = sb;
+    hint.se = se;
   }
-  int s = lo;
-  unsigned long long sb = src.begin[s], se = src.begin[s + 1];
   const Elem* base = static_cast<const Elem*>(src.ptr[s]);
   const Elem* p = base + (ge - sb);
   F8 x;
@@ -498,6 +513,13 @@ __device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned
     }
   }
   return x;
+}
+
+// Without a hint (the multi-rank kernels: the W slices one thread touches are far apart, a hint would only cost registers).
+template <int MODE>
+__device__ __forceinline__ F8 load_src(const Src& src, const void* buf, unsigned long long e, unsigned long long n, bool aligned) {
+  SegHint none;
+  return load_src<MODE>(src, none, buf, e, n, aligned);
 }
 
 // peer[jj] for a RUNTIME jj without putting the parameter block into local memory (select chain)

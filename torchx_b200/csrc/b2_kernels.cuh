@@ -4,26 +4,33 @@
 
 #include "b2_dev.cuh"
 
-// W == 1 (and the single-GPU roofline probe): x <- round(wire(scale * x)), one streaming pass.
+// W == 1 (and the single-GPU roofline probe): x <- round(wire(scale * x)), one streaming pass.  Each CTA owns a contiguous
+// range of vecs and a thread's successive vecs are 512 apart (a warp still reads 1 KiB of consecutive memory per access):
+// when the input comes through a segment table (zero-copy bucket fill) a thread then stays inside one parameter for many
+// trips and its segment hint keeps hitting.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) k_local_pass(const __grid_constant__ Src src, void* buf, unsigned long long n, float scale) {
   using namespace dev;
   const bool aligned = buf_aligned<MODE>(buf);
   const unsigned long long V = (n + 7) / 8;
-  const unsigned long long stride = static_cast<unsigned long long>(gridDim.x) * kThreads;
   constexpr int U = 4;
-  for (unsigned long long v0 = static_cast<unsigned long long>(blockIdx.x) * kThreads + threadIdx.x;
-       v0 < V; v0 += stride * U) {
+  constexpr unsigned long long kTrip = static_cast<unsigned long long>(kThreads) * U;
+  const unsigned long long per_cta = (V + gridDim.x - 1) / gridDim.x;
+  const unsigned long long span = (per_cta + kTrip - 1) / kTrip * kTrip;
+  const unsigned long long lo = blockIdx.x * span;
+  const unsigned long long hi = lo + span < V ? lo + span : V;
+  SegHint hint;
+  for (unsigned long long v0 = lo + threadIdx.x; v0 < hi; v0 += kTrip) {
     F8 x[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const unsigned long long v = v0 + u * stride;
-      if (v < V) x[u] = load_src<MODE>(src, buf, v * 8, n, aligned);
+      const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kThreads;
+      if (v < hi) x[u] = load_src<MODE>(src, hint, buf, v * 8, n, aligned);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const unsigned long long v = v0 + u * stride;
-      if (v < V) {
+      const unsigned long long v = v0 + static_cast<unsigned long long>(u) * kThreads;
+      if (v < hi) {
         const Wire<MODE> c = compress<MODE>(x[u], scale);
         store_out<MODE>(buf, v * 8, n, aligned, finalize<MODE>(widen<MODE>(c)));
       }

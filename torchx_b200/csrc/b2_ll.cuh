@@ -124,30 +124,32 @@ __global__ void __launch_bounds__(kThreads, 1)
       const bool do3 = v0 >= step + first && v0 - step < Ls;
       if (!do2 && !do3) break;
       if (do2) {  // ---- phase 2: reduce my slice as its contributions arrive, push the result to everyone
-        Wire<MODE> w[U][W];
-        bool pend[U][W];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const unsigned long long v = v0 + u * stride;
-#pragma unroll
-          for (int r = 0; r < W; ++r) {
-            pend[u][r] = false;
-            if (v < Ls && base + v < V) w[u][r] = wire_poll<MODE>(mine + base_ll + r * c.slice_cap + v * WVB, &pend[u][r]);
-          }
-        }
+        // G contributions of one vec are polled together (all W for the 16-byte bf16 wire vecs; 4 for the 32-byte fp32 ones,
+        // which would not fit the register file otherwise); accumulation stays in rank order either way.
+        constexpr int G = (MODE == B2_F32 && W > 4) ? 4 : W;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const unsigned long long v = v0 + u * stride;
           if (v < Ls && base + v < V) {
+            F8 s;
 #pragma unroll
-            for (int r = 0; r < W; ++r) {
-              const uint8_t* p = mine + base_ll + r * c.slice_cap + v * WVB;
-              if (pend[u][r]) ll::wait_vec<MODE>(c, p, w[u][r], true);
-              wire_reset<MODE>(const_cast<uint8_t*>(p));  // back to "not written yet" for the collective after next
+            for (int r0 = 0; r0 < W; r0 += G) {
+              Wire<MODE> w[G];
+              bool pend[G];
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                if (r0 + g < W) w[g] = wire_poll<MODE>(mine + base_ll + (r0 + g) * c.slice_cap + v * WVB, &pend[g]);
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                if (r0 + g < W) {
+                  uint8_t* p = mine + base_ll + (r0 + g) * c.slice_cap + v * WVB;
+                  if (pend[g]) ll::wait_vec<MODE>(c, p, w[g], true);
+                  wire_reset<MODE>(p);  // back to "not written yet" for the collective after next
+                  if (r0 + g == 0) s = widen<MODE>(w[g]);
+                  else accumulate(s, widen<MODE>(w[g]));  // rank order, fp32
+                }
+              }
             }
-            F8 s = widen<MODE>(w[u][0]);
-#pragma unroll
-            for (int r = 1; r < W; ++r) accumulate(s, widen<MODE>(w[u][r]));  // rank order, fp32
             const Wire<MODE> q = wire_no_sentinel<MODE>(finalize<MODE>(s));
 #pragma unroll
             for (int jj = 0; jj < W; ++jj) st_wire<MODE>(c.peer[jj] + my_out + v * WVB, q);
@@ -156,34 +158,33 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       if (do3) {  // ---- phase 3: widen every slice of the previous trip as it arrives
         const unsigned long long p0 = v0 - step;
-        Wire<MODE> w[U][W];
-        bool pend[U][W];
+        constexpr int G = (MODE == B2_F32 && W > 4) ? 4 : W;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const unsigned long long v = p0 + u * stride;
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) {
-            int j = c.rank + jj;
-            if (j >= W) j -= W;
-            const unsigned long long gv = j * Ls + v;
-            pend[u][jj] = false;
-            if (v < Ls && gv < V)
-              w[u][jj] = wire_poll<MODE>(mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB, &pend[u][jj]);
-          }
-        }
+          for (int j0 = 0; j0 < W; j0 += G) {
+            Wire<MODE> w[G];
+            bool pend[G];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const unsigned long long v = p0 + u * stride;
+            for (int g = 0; g < G; ++g) {
+              int j = c.rank + j0 + g;
+              if (j >= W) j -= W;
+              pend[g] = false;
+              if (j0 + g < W && v < Ls && j * Ls + v < V)
+                w[g] = wire_poll<MODE>(mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB, &pend[g]);
+            }
 #pragma unroll
-          for (int jj = 0; jj < W; ++jj) {
-            int j = c.rank + jj;
-            if (j >= W) j -= W;
-            const unsigned long long gv = j * Ls + v;
-            if (v < Ls && gv < V) {
-              uint8_t* p = mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB;
-              if (pend[u][jj]) ll::wait_vec<MODE>(c, p, w[u][jj], true);
-              store_out<MODE>(buf, gv * 8, n, aligned, w[u][jj]);
-              wire_reset<MODE>(p);
+            for (int g = 0; g < G; ++g) {
+              int j = c.rank + j0 + g;
+              if (j >= W) j -= W;
+              const unsigned long long gv = j * Ls + v;
+              if (j0 + g < W && v < Ls && gv < V) {
+                uint8_t* p = mine + base_ll + (static_cast<unsigned long long>(W) + j) * c.slice_cap + v * WVB;
+                if (pend[g]) ll::wait_vec<MODE>(c, p, w[g], true);
+                store_out<MODE>(buf, gv * 8, n, aligned, w[g]);
+                wire_reset<MODE>(p);
+              }
             }
           }
         }

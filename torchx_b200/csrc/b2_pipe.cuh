@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (tid < kAS) {
     // ================= role A data: cast (NVLS) / scatter (P2P) =================
     const int t = tid - kA0;
-    if (t == 0) trace_stamp(c, 0);
+      if (t == 0) trace_stamp(c, 0);
     for (int k = 0; k < nk; ++k) {
       const unsigned long long lo = (static_cast<unsigned long long>(k) * g + b) * cell;
       const unsigned long long hi = lo + cell < Ls ? lo + cell : Ls;
