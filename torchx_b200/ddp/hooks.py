@@ -17,7 +17,11 @@ from .comm import Communicator
 
 class B200HookState:
     def __init__(self, comm: Optional[Communicator] = None, wire: str = "bf16", algo: str = "auto") -> None:
-        self.comm = comm if comm is not None else Communicator.from_env()
+        if comm is None:  # one communicator per process: reuse the one init_pg("b200") created (each owns a multi-GiB arena)
+            from torchx_b200 import distributed as _dist
+
+            comm = _dist._COMM if _dist._COMM is not None else Communicator.from_env()
+        self.comm = comm
         self.wire = wire
         self.algo = algo
         self.device = torch.device("cuda", self.comm.device)
