@@ -33,7 +33,7 @@ class _Finder:
                 mod = importlib.import_module("torchx_b200" + name[len("torchx"):])
             except Exception:
                 return None
-            sys.modules[name] = mod
+            # NOT sys.modules[name] = mod here: importlib would then take mod.__spec__ and load a second copy
             return importlib.util.spec_from_loader(name, loader=_Loader(mod))
         return None
 sys.meta_path.insert(0, _Finder())
@@ -70,7 +70,7 @@ class TestWithTmpDir(unittest.TestCase):
 PATCHES = [  # (regex, replacement) applied to every copied test file
     (r"from torchx\.test\.fixtures import TestWithTmpDir", FIXTURE),
     (r"from torchx\.specs import named_resources, named_resources_aws, resource", "from torchx.specs import named_resources, resource\nnamed_resources_aws = None"),
-    (r"    TORCHX_HOME,\n    Workspace,\n\)", "    )\nTORCHX_HOME = Workspace = None"),
+    (r"    TORCHX_HOME,\n    Workspace,\n\)", "    TORCHX_HOME,\n)\nWorkspace = None"),
     (r"    UnknownAppException,\n    Workspace,\n\)", "    UnknownAppException,\n)\nWorkspace = None"),
     (r"from torchx\.specs import AppDef, AppDryRunInfo, CfgVal, runopts, Workspace", "from torchx.specs import AppDef, AppDryRunInfo, CfgVal, runopts\nWorkspace = None"),
     (r"from torchx\.tracker\.api import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID", "from torchx.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID"),
@@ -85,12 +85,21 @@ FILES = [
     "util/test/types_test.py", "schedulers/test/ids_test.py", "schedulers/test/streams_test.py", "specs/test/api_test.py",
     "specs/test/builders_test.py", "components/test/dist_test.py", "components/test/structured_arg_test.py",
     "schedulers/test/local_scheduler_test.py", "runner/test/config_test.py", "runner/test/api_test.py",
+    "schedulers/test/api_test.py", "schedulers/test/registry_test.py", "distributed/test/dist_test.py", "specs/test/finder_test.py",
+    "specs/test/named_resources_generic_test.py", "apps/utils/test/process_monitor_test.py", "util/test/strings_test.py",
+    "cli/test/cmd_run_test.py", "cli/test/cmd_log_test.py", "cli/test/cmd_status_test.py", "cli/test/cmd_describe_test.py",
+    "cli/test/cmd_cancel_test.py", "cli/test/cmd_list_test.py", "cli/test/cmd_runopts_test.py", "cli/test/cmd_configure_test.py",
+    "cli/test/main_test.py", "cli/test/argparse_util_test.py",
 ]
+ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]
+if ONLY:
+    FILES = [f for f in FILES if any(o in f for o in ONLY)]
 
 
 def main() -> None:
     if not os.path.isdir(REF):
         raise SystemExit(f"{REF} is not available here")
+    keep = "--keep" in sys.argv  # leave the prepared directory behind (path printed) to re-run single tests by hand
     work = tempfile.mkdtemp(prefix="ref_tests_")
     try:
         with open(os.path.join(work, "conftest.py"), "w") as f:
@@ -116,7 +125,10 @@ def main() -> None:
                     print("      " + ln[:150])
         print(f"TOTAL: {total_p} passed, {total_f} failed")
     finally:
-        shutil.rmtree(work, ignore_errors=True)
+        if keep:
+            print(f"kept: {work}")
+        else:
+            shutil.rmtree(work, ignore_errors=True)
 
 
 if __name__ == "__main__":

@@ -4,7 +4,8 @@ Stand-alone counterpart of the gang-level ``-cfg job_timeout=...,exit_on_file=..
 ``local_cuda`` scheduler, for wrapping a single role's entrypoint the way the reference's
 ``python -m torchx.apps.utils.process_monitor`` is used (torchx/apps/utils/process_monitor.py:20-118): same flags, same exit
 code 34 when the limit is hit before the program was started, SIGTERM first and SIGKILL after ``--kill_timeout``.
-Sentinels are local paths (the reference resolves them through fsspec; remote stores are out of this path's scope).
+Sentinels are local paths, or ``scheme://`` URLs resolved through fsspec as in the reference (fsspec must then be
+installed).  The progress lines printed to stdout are the reference's, so log greps written for it keep working.
 
     python -m torchx_b200.apps.utils.process_monitor --timeout 3600 --exit_on_file /tmp/stop -- python train.py
 """
@@ -32,6 +33,15 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
+def _exists(path: str) -> bool:
+    if "://" not in path:
+        return os.path.exists(path)
+    import fsspec  # only needed for URL sentinels; a missing fsspec is an error, not "file absent"
+
+    fs, fs_path = fsspec.core.url_to_fs(path)
+    return bool(fs.exists(fs_path))
+
+
 def supervise(entrypoint: str, args: List[str], timeout: Optional[float] = None, start_on_file: Optional[str] = None,
               exit_on_file: Optional[str] = None, poll_rate: float = 5.0, kill_timeout: float = 60.0) -> int:
     """Returns the exit code the monitor itself should exit with."""
@@ -40,35 +50,39 @@ def supervise(entrypoint: str, args: List[str], timeout: Optional[float] = None,
     def expired() -> bool:
         return bool(timeout) and time.monotonic() - t0 > timeout  # type: ignore[operator]
 
-    while start_on_file and not os.path.exists(start_on_file):
+    while start_on_file:
+        if _exists(start_on_file):
+            print(f"{start_on_file} exists, starting process...", flush=True)
+            break
         if expired():
-            print("time limit reached before the start file appeared; not launching", flush=True)
+            print("reached timeout before launching, terminating...", flush=True)
             return TIMEOUT_EXIT_CODE
         time.sleep(poll_rate)
     if args and args[0] == "--":
         args = args[1:]
     proc = subprocess.Popen([entrypoint, *args])
-    print(f"process_monitor: pid {proc.pid}", flush=True)
+    print(f"started process {proc.pid}", flush=True)
     while True:
         try:
             rc = proc.wait(poll_rate)
-            print(f"process_monitor: exit code {rc}", flush=True)
+            print(f"process exited with exit code {rc}", flush=True)
             return rc
         except subprocess.TimeoutExpired:
             if expired():
-                print("process_monitor: time limit reached", flush=True)
+                print("reached timeout, terminating...", flush=True)
                 break
-            if exit_on_file and os.path.exists(exit_on_file):
-                print(f"process_monitor: {exit_on_file} exists", flush=True)
+            if exit_on_file and _exists(exit_on_file):
+                print(f"{exit_on_file} exists, terminating...", flush=True)
                 break
     proc.terminate()
+    print("issued terminate, waiting for exit...", flush=True)
     try:
         proc.wait(kill_timeout)
     except subprocess.TimeoutExpired:
-        print("process_monitor: still alive after the grace period, killing", flush=True)
+        print("reached safe termination timeout, killing...", flush=True)
         proc.kill()
     rc = proc.wait()
-    print(f"process_monitor: exit code {rc}", flush=True)
+    print(f"process exited with exit code {rc}", flush=True)
     return rc
 
 

@@ -14,33 +14,13 @@ import sys
 import traceback
 from typing import Any, Callable, Dict, List, Optional
 
-_SCHEDULERS: Dict[str, Callable[..., Any]] = {}
-_NAMED_RESOURCES: Dict[str, Callable[[], Any]] = {}
+from torchx_b200.plugins._registration import NAMED_RESOURCES as _NAMED_RESOURCES
+from torchx_b200.plugins._registration import SCHEDULERS as _SCHEDULERS
+from torchx_b200.plugins._registration import register, resource_tags  # noqa: F401
+
 _ERRORS: List[Dict[str, str]] = []
 _DISCOVERED = False
 NAMESPACE = "torchx_b200_plugins"
-
-
-class register:
-    """Decorators used INSIDE plugin modules."""
-
-    @staticmethod
-    def scheduler(name: Optional[str] = None) -> Callable[[Callable[..., Any]], Callable[..., Any]]:
-        """Register ``fn(session_name, **kwargs) -> Scheduler`` under ``name`` (default: the function name)."""
-
-        def deco(fn: Callable[..., Any]) -> Callable[..., Any]:
-            _SCHEDULERS[name or fn.__name__] = fn
-            return fn
-
-        return deco
-
-    @staticmethod
-    def named_resource(name: Optional[str] = None) -> Callable[[Callable[[], Any]], Callable[[], Any]]:
-        def deco(fn: Callable[[], Any]) -> Callable[[], Any]:
-            _NAMED_RESOURCES[name or fn.__name__] = fn
-            return fn
-
-        return deco
 
 
 def _discover() -> None:

@@ -6,6 +6,7 @@ from .api import (  # noqa: F401
     MISSING,
     NONE,
     NULL_RESOURCE,
+    TORCHX_HOME,
     AppDef,
     AppDryRunInfo,
     AppHandle,

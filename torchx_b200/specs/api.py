@@ -7,8 +7,13 @@ Out of scope here (cloud / container only): mounts, Wo
 """
 from __future__ import annotations
 
+import asyncio
 import copy
+import inspect
 import json
+import logging
+import os
+import pathlib
 import re
 import string
 from dataclasses import asdict, dataclass, field, fields
@@ -25,6 +30,16 @@ ALL: str = "all"  # "any scheduler backend"
 MISSING: str = "<MISSING>"  # a required string attribute that was not provided
 NONE: str = "<NONE>"  # an optional string attribute that is unset
 
+logger = logging.getLogger(__name__)
+
+
+def TORCHX_HOME(*subdir_paths: str) -> pathlib.Path:
+    """The launcher's dot-directory (``$TORCHX_HOME``, else ``~/.torchx``), optionally a sub-directory of it; created on
+    demand (reference torchx/specs/api.py:68-89)."""
+    home = pathlib.Path(os.environ.get("TORCHX_HOME") or pathlib.Path.home() / ".torchx").joinpath(*subdir_paths)
+    home.mkdir(parents=True, exist_ok=True)
+    return home
+
 
 # ---------------------------------------------------------------------------------------------------------------
 # resources
@@ -39,6 +54,19 @@ class Resource:
     capabilities: Dict[str, Any] = field(default_factory=dict)
     devices: Dict[str, int] = field(default_factory=dict)
     tags: Dict[str, object] = field(default_factory=dict)
+
+    def is_fractional(self) -> bool:
+        """True when a named-resource registration tagged this as a slice of a bigger host (reference api.py:127-135)."""
+        from torchx_b200.plugins._registration import resource_tags
+
+        return bool(self.tags.get(resource_tags.IS_FRACTIONAL, False))
+
+    def get_resource_name(self) -> Optional[str]:
+        """The name this resource was registered under, if it came from ``register.named_resource`` (api.py:137-146)."""
+        from torchx_b200.plugins._registration import resource_tags
+
+        name = self.tags.get(resource_tags.RESOURCE_NAME)
+        return None if name is None else str(name)
 
     @staticmethod
     def copy(original: "Resource", **capabilities: Any) -> "Resource":
@@ -92,8 +120,17 @@ class macros:
             return node
 
         def apply(self, role: "Role") -> "Role":
-            """A deep copy of ``role`` with every macro resolved."""
-            out = copy.deepcopy(role)
+            """A deep copy of ``role`` with every macro resolved.  Lazy ``overrides`` (callables / awaitables) cannot be
+            deep-copied: they are carried over by reference, as the reference does (api.py:232-243)."""
+            lazy = role.overrides
+            if lazy:
+                logger.warning("Role overrides are not supported for macros. Overrides will not be copied")
+            role.overrides = {}
+            try:
+                out = copy.deepcopy(role)
+            finally:
+                role.overrides = lazy
+            out.overrides = lazy
             out.args = [self.substitute(a) for a in out.args]
             out.env = {k: self.substitute(v) for k, v in out.env.items()}
             out.metadata = self._walk(out.metadata)
@@ -129,6 +166,23 @@ class Role:
     metadata: Dict[str, Any] = field(default_factory=dict)
     mounts: List[Any] = field(default_factory=list)
     workspace: Optional[Any] = None
+    # Deprecated in TorchX but still honoured: {attribute name: zero-arg callable | awaitable} evaluated on first read
+    # of that attribute, then cached (reference api.py:469-487).
+    overrides: Dict[str, Any] = field(default_factory=dict)
+
+    def __getattribute__(self, attrname: str) -> Any:
+        get = super().__getattribute__
+        if attrname != "overrides" and not attrname.startswith("__"):
+            try:
+                lazy = get("overrides")
+            except AttributeError:  # during dataclass __init__, before the field is assigned
+                lazy = None
+            if lazy and attrname in lazy:
+                pending = lazy[attrname]
+                value = asyncio.get_event_loop().run_until_complete(pending) if inspect.isawaitable(pending) else pending()
+                object.__setattr__(self, attrname, value)
+                lazy[attrname] = lambda: value
+        return get(attrname)
 
     def pre_proc(self, scheduler: str, dryrun_info: "AppDryRunInfo") -> "AppDryRunInfo":
         """Per-role hook to amend the scheduler request; called by ``Scheduler.submit_dryrun`` in role order."""
@@ -198,17 +252,25 @@ class RoleStatus:
         return {"role": self.role, "replicas": [asdict(r) for r in self.replicas]}
 
 
+# ``ExcType('On WorkerInfo(...):\n<lines>\n')`` - the envelope torch.distributed.rpc wraps remote errors in; and a message
+# followed by a C++ ``Exception raised from ...`` trailer.  Only the informative part is shown by ``torchx status``.
+_RPC_ENVELOPE = re.compile(r"\w*\('On WorkerInfo\(.+\):\n(.*\n)*'\)")
+_CPP_TRAILER = re.compile(r"(?P<msg>.+)\nException.*")
+
+
 def _wrap(text: str, header: str, width: int = 80) -> str:
-    lines, cur = [], ""
-    for word in text.split(" "):
-        if cur and len(cur) + 1 + len(word) > width:
-            lines.append(cur)
-            cur = word
-        else:
-            cur = f"{cur} {word}" if cur else word
-    lines.append(cur)
+    """Soft-wrap as the reference's status printer does (api.py:663-684): a line runs to the first space at or after
+    ``width`` characters, the space starts the next line; ``header`` leads the first line, blanks of its width the rest."""
+    assert len(header) < width
+    m = _RPC_ENVELOPE.search(text)
+    if m:
+        text = m.group(0)
+    m = _CPP_TRAILER.search(text)
+    if m:
+        text = m.group("msg")
+    pieces = re.findall(r"(?s).{%d}[^ ]*|.+" % width, text) or [""]
     pad = " " * len(header)
-    return "\n".join((header if i == 0 else pad) + ln for i, ln in enumerate(lines))
+    return "\n".join((header if i == 0 else pad) + piece for i, piece in enumerate(pieces))
 
 
 @dataclass
@@ -238,6 +300,9 @@ class AppStatus:
             "structured_error_msg": self.structured_error_msg,
             "url": self.ui_url,
         }
+
+    def _format_error_message(self, msg: str, header: str, width: int = 80) -> str:
+        return _wrap(msg, header, width)
 
     def _select(self, filter_roles: Optional[List[str]]) -> List[RoleStatus]:
         return [r for r in self.roles if not filter_roles or r.role in filter_roles]
