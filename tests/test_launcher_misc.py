@@ -4,6 +4,7 @@ import argparse
 import io
 import json
 import os
+import re
 import subprocess
 import sys
 import textwrap
@@ -201,7 +202,21 @@ def test_cli_dryrun_runopts_builtins_and_run(tmp_path, capsys):
     env = dict(os.environ, PYTHONPATH=ROOT)
     ok = subprocess.run([sys.executable, "-m", "torchx_b200.cli.main", "run", "-s", "local_cwd", "-cfg", f"log_dir={tmp_path}", "utils.echo", "--msg", "from-cli"],
                         capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=120)
-    assert ok.returncode == 0 and ok.stdout.startswith("local_cwd://torchx/echo-") and "echo/0 from-cli" in ok.stderr
+    plain = re.sub(r"\x1b\[[0-9;]*m", "", ok.stderr)  # the role/replica prefix is coloured, as in the reference (cli/cmd_log.py:66)
+    assert ok.returncode == 0 and ok.stdout.startswith("local_cwd://torchx/echo-") and "echo/0 from-cli" in plain
+    # --tee_logs: same lines through util.log_tee_helpers (uncoloured when stderr is not a tty)
+    tee = subprocess.run([sys.executable, "-m", "torchx_b200.cli.main", "run", "-s", "local_cwd", "-cfg", f"log_dir={tmp_path}", "--tee_logs", "utils.echo",
+                          "--msg", "teed"], capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=120)
+    assert tee.returncode == 0 and "echo/0 teed" in tee.stderr
+    # --stdin: the whole request as JSON (reference cmd_run.py:365-392); any other option next to it is an error
+    req = json.dumps({"scheduler": "local_cwd", "scheduler_args": {"log_dir": str(tmp_path)}, "component_name": "utils.echo",
+                      "component_args": {"msg": "from-json"}})
+    js = subprocess.run([sys.executable, "-m", "torchx_b200.cli.main", "run", "--stdin"], input=req, capture_output=True, text=True, env=env,
+                        cwd=str(tmp_path), timeout=120)
+    assert js.returncode == 0 and "from-json" in js.stderr, js.stderr
+    clash = subprocess.run([sys.executable, "-m", "torchx_b200.cli.main", "run", "--stdin", "--wait"], input=req, capture_output=True, text=True,
+                           env=env, cwd=str(tmp_path), timeout=120)
+    assert clash.returncode == 2 and "Cannot specify --wait when using --stdin" in clash.stderr
     bad = subprocess.run([sys.executable, "-m", "torchx_b200.cli.main", "run", "-s", "local_cuda", "utils.sh", "exit", "3"],
                          capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=120)
     assert bad.returncode == 1 and "FAILED" in bad.stderr

@@ -10,12 +10,14 @@ import sys
 import threading
 import time
 from queue import Queue
-from typing import List, Optional, TextIO, Tuple
+from typing import Optional, TextIO
 
 from torchx_b200.cli.cmd_base import SubCommand
 from torchx_b200.runner import Runner, get_runner
 from torchx_b200.schedulers.api import Stream
-from torchx_b200.specs.api import AppDef, is_started, make_app_handle
+from torchx_b200.specs.api import is_started, make_app_handle
+from torchx_b200.util.log_tee_helpers import _find_role_replicas as find_role_replicas
+from torchx_b200.util.log_tee_helpers import _prefix_line
 
 logger = logging.getLogger(__name__)
 ID_FORMAT = "SCHEDULER://[SESSION_NAME]/APP_ID/[ROLE_NAME/[REPLICA_IDS,...]]"
@@ -29,17 +31,13 @@ def validate(identifier: str) -> None:
         sys.exit(1)
 
 
-def find_role_replicas(app: AppDef, role_name: Optional[str]) -> List[Tuple[str, int]]:
-    return [(role.name, k) for role in app.roles if role_name is None or role.name == role_name for k in range(role.num_replicas)]
-
-
 def print_log_lines(file: TextIO, runner: Runner, app_handle: str, role_name: str, replica_id: int, regex: Optional[str],
-                    should_tail: bool, exceptions: "Queue[Exception]", streams: Optional[Stream], colorize: bool = False) -> None:
-    prefix = f"{GREEN}{role_name}/{replica_id}{ENDC} " if colorize else f"{role_name}/{replica_id} "
+                    should_tail: bool, exceptions: "Queue[Exception]", streams: Optional[Stream]) -> None:
+    prefix = f"{GREEN}{role_name}/{replica_id}{ENDC} "  # always coloured, as the reference prints it (cmd_log.py:66)
     try:
         for line in runner.log_lines(app_handle, role_name, replica_id, regex, should_tail=should_tail, streams=streams):
             try:
-                print(prefix + line, file=file, end="", flush=True)
+                print(_prefix_line(prefix, line), file=file, end="", flush=True)
             except BrokenPipeError:
                 return
     except Exception as e:  # noqa: BLE001 - surfaced by get_logs in the caller's thread
@@ -75,8 +73,7 @@ def get_logs(file: TextIO, identifier: str, regex: Optional[str], should_tail: b
             logger.error(f"No role [{role_name}] found for app: {app.name}. Roles: {[r.name for r in app.roles]}")
             sys.exit(1)
     errors: "Queue[Exception]" = Queue()
-    colorize = hasattr(file, "isatty") and file.isatty()
-    threads = [threading.Thread(target=print_log_lines, args=(file, runner, handle, r, k, regex, should_tail, errors, streams, colorize), daemon=True)
+    threads = [threading.Thread(target=print_log_lines, args=(file, runner, handle, r, k, regex, should_tail, errors, streams), daemon=True)
                for r, k in targets]
     for t in threads:
         t.start()

@@ -24,8 +24,15 @@ _COMM: Optional[Any] = None  # torchx_b200.ddp.Communicator when init_pg("b200")
 
 
 def local_rank() -> int:
-    """``LOCAL_RANK`` (0 when not launched by torchrun / local_cuda)."""
-    return int(os.environ.get("LOCAL_RANK", "0"))
+    """``LOCAL_RANK``; 0 when the launcher did not set it - with a warning if a process group is nevertheless up, because
+    then every process of the node would claim device 0 (reference torchx/distributed/__init__.py:26-54)."""
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    if dist.is_available() and dist.is_initialized():
+        warnings.warn("the default torch.distributed process group is initialized but the `LOCAL_RANK` environment variable is "
+                      "not set: local_rank() trivially returns 0.  Launch the script with torchx (local_cuda / local_cwd) or "
+                      "torchrun, or set `LOCAL_RANK` yourself.")
+    return 0
 
 
 def rank() -> int:
@@ -80,6 +87,7 @@ def init_pg(backend: str = "auto", **kwargs: Any) -> torch.device:
 
     ``auto``: nccl when CUDA devices exist, gloo otherwise (reference behaviour).  When the process was not launched
     by a torchrun-compatible launcher a trivial single-rank group is created so scripts also run with plain ``python``.
+    As in the reference the caller selects the returned device (``torch.cuda.set_device`` / ``.to(device)``).
     ``b200``: rendezvous through the ``local_cuda`` scheduler's shm control block and CUDA IPC; no process group.
     """
     global _COMM
@@ -90,20 +98,16 @@ def init_pg(backend: str = "auto", **kwargs: Any) -> torch.device:
             _COMM = Communicator.from_env(**kwargs)
         return torch.device("cuda", _COMM.device)
     if backend == "auto":
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
-    if dist.is_initialized():
-        warnings.warn("the default process group is already initialized; init_pg() leaves it untouched")
-    elif is_torchelastic_launched():
+        # a CUDA build of torch says is_available() on some CPU hosts: ask for actual devices and for NCCL itself
+        has_gpu = torch.cuda.is_available() and torch.cuda.device_count() > 0 and dist.is_nccl_available()
+        backend = "nccl" if has_gpu else "gloo"
+    if is_torchelastic_launched():
         dist.init_process_group(backend=backend, **kwargs)
-    else:
-        warnings.warn("not launched by torchrun/local_cuda: creating a trivial single-rank process group")
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "0")
+    else:  # plain `python script.py`: a one-rank group on a free port, so the same script runs either way
+        os.environ["MASTER_ADDR"] = "localhost"
+        os.environ["MASTER_PORT"] = "0"
         dist.init_process_group(backend=backend, rank=0, world_size=1, **kwargs)
-    dev = local_cuda_device() if backend == "nccl" else torch.device("cpu")
-    if dev.type == "cuda":
-        torch.cuda.set_device(dev)
-    return dev
+    return local_cuda_device() if backend == "nccl" else torch.device("cpu")
 
 
 def barrier() -> None:

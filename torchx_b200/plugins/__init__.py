@@ -1,73 +1,60 @@
-"""Minimal plugin registry: ``@register.scheduler()`` / ``@register.named_resource()`` plus discovery of the
-``torchx_b200_plugins.{schedulers,named_resources}`` namespace packages on ``sys.path``.
+"""Plugins: add scheduler names and named resources without editing this package.
 
-Mirrors the part of reference torchx/plugins (_registration.py:187-274 decorators, _registry.py:83-515 discovery with
-error capture) that the launch path touches: a scheduler module anywhere on the path can add or override scheduler
-names without editing this package; modules that fail to import are recorded, not fatal.  Tracker plugins and the
-fractional named-resource machinery are out of scope.
+Put ``@register``-decorated factories in modules under the ``torchx_b200_plugins.{schedulers,named_resources}`` namespace
+packages anywhere on ``sys.path`` (or publish them as ``torchx_b200.schedulers`` / ``torchx_b200.named_resources`` entry
+points); ``plugins.registry()`` discovers them lazily, and ``print(plugins.registry())`` is a YAML report including the
+modules that failed to import.  Registered schedulers REPLACE the built-in scheduler map, as in TorchX.
+
+Same public names as reference torchx/plugins/__init__.py:36-70 (``register``, ``resource_tags``, the fractional helpers,
+``PluginRegistry``, ``PluginType``, ``RegistrationError``, ``registry``); tracker plugins are out of scope.
 """
 from __future__ import annotations
 
-import importlib
-import pkgutil
 import sys
-import traceback
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Callable, Dict, List
 
-from torchx_b200.plugins._registration import NAMED_RESOURCES as _NAMED_RESOURCES
-from torchx_b200.plugins._registration import SCHEDULERS as _SCHEDULERS
-from torchx_b200.plugins._registration import register, resource_tags  # noqa: F401
+from torchx_b200.plugins._registration import (  # noqa: F401
+    EIGHTH,
+    HALF,
+    QUARTER,
+    SIXTEENTH,
+    WHOLE,
+    halve_mem_down_to,
+    powers_of_two_gpus,
+    register,
+    resource_tags,
+)
+from torchx_b200.plugins._registry import (  # noqa: F401
+    NAMESPACE,
+    PluginRegistry,
+    PluginSource,
+    PluginType,
+    RegistrationError,
+    registry,
+)
 
-_ERRORS: List[Dict[str, str]] = []
-_DISCOVERED = False
-NAMESPACE = "torchx_b200_plugins"
-
-
-def _discover() -> None:
-    global _DISCOVERED
-    if _DISCOVERED:
-        return
-    _DISCOVERED = True
-    for group in ("schedulers", "named_resources"):
-        pkg_name = f"{NAMESPACE}.{group}"
-        try:
-            pkg = importlib.import_module(pkg_name)
-        except ModuleNotFoundError:
-            continue
-        except Exception:  # a broken namespace package must not take the launcher down
-            _ERRORS.append({"module": pkg_name, "error": traceback.format_exc()})
-            continue
-        for info in pkgutil.iter_modules(getattr(pkg, "__path__", [])):
-            if info.name.startswith("_"):
-                continue
-            mod = f"{pkg_name}.{info.name}"
-            try:
-                importlib.import_module(mod)
-            except Exception:
-                _ERRORS.append({"module": mod, "error": traceback.format_exc()})
+__all__ = ["register", "resource_tags", "powers_of_two_gpus", "halve_mem_down_to", "WHOLE", "HALF", "QUARTER", "EIGHTH", "SIXTEENTH",
+           "RegistrationError", "PluginType", "PluginSource", "PluginRegistry", "registry"]
 
 
+# -- convenience wrappers used inside this package ------------------------------------------------------------------
 def registered_schedulers() -> Dict[str, Callable[..., Any]]:
-    _discover()
-    return dict(_SCHEDULERS)
+    return dict(registry().get(PluginType.SCHEDULER))
 
 
 def registered_named_resources() -> Dict[str, Callable[[], Any]]:
-    _discover()
-    return dict(_NAMED_RESOURCES)
+    return dict(registry().get(PluginType.NAMED_RESOURCE))
 
 
 def errors() -> List[Dict[str, str]]:
-    """Plugin modules that failed to import (for ``torchx runopts`` / diagnostics)."""
-    _discover()
-    return list(_ERRORS)
+    """Plugin modules that failed to import / plugins that were rejected, as plain dicts."""
+    reg = registry()
+    reg.info()
+    return [{"module": e.module, "error": e.error, **({"name": e.name} if e.name else {})} for e in reg.errors]
 
 
 def reset_for_tests() -> None:
-    global _DISCOVERED
-    _SCHEDULERS.clear()
-    _NAMED_RESOURCES.clear()
-    _ERRORS.clear()
-    _DISCOVERED = False
+    """Drop the cached registry and the imported plugin namespace (so a changed ``sys.path`` is re-scanned)."""
+    registry().clear()
     for name in [m for m in sys.modules if m == NAMESPACE or m.startswith(NAMESPACE + ".")]:
         del sys.modules[name]

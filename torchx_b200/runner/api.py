@@ -131,7 +131,9 @@ class Runner:
         if not app.roles:
             raise ValueError(f"No roles for app: {app.name}. Did you forget to add roles to AppDef?")
         if workspace:
-            raise NotImplementedError("workspaces are not supported by the local schedulers (cwd is the image)")
+            # Only image-building schedulers consume a workspace (reference runner/api.py:405-424 applies it to
+            # WorkspaceMixin schedulers only); the local ones run from the cwd, so like the reference it is ignored.
+            logger.debug("workspace `%s` ignored: `%s` runs from the current directory", workspace, scheduler)
         parent_run_id = os.environ.get(ENV_TORCHX_PARENT_RUN_ID, parent_run_id)
         for role in app.roles:
             if not role.entrypoint:

@@ -1,4 +1,5 @@
 """``torchx_b200.specs`` - the data model components and schedulers share (reference torchx/specs/__init__.py)."""
+import difflib
 from typing import Callable, Dict, Optional
 
 from .api import (  # noqa: F401
@@ -35,7 +36,7 @@ from .api import (  # noqa: F401
     runopt,
     runopts,
 )
-from .named_resources import NAMED_RESOURCES as _GENERIC
+from .named_resources_generic import NAMED_RESOURCES as _GENERIC
 
 GiB: int = 1024
 
@@ -56,10 +57,12 @@ class _NamedResources:
 
     def __getitem__(self, key: str) -> Resource:
         table = _all_named_resources()
-        if key.upper() == "MISSING":
+        if key.upper() in ("MISSING", "NULL"):
             return NULL_RESOURCE
         if key not in table:
-            raise KeyError(f"No named resource found for `{key}`. Registered named resources: {sorted(table)}")
+            close = difflib.get_close_matches(key, table.keys(), n=1)
+            hint = f"Did you mean `{close[0]}`?" if close else f"Registered named resources: {sorted(table)}"
+            raise KeyError(f"No named resource found for `{key}`. {hint}")
         return table[key]()
 
     def __contains__(self, key: str) -> bool:

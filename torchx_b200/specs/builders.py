@@ -29,13 +29,16 @@ def get_fn_docstring(fn: Callable[..., object]) -> Tuple[str, Dict[str, str]]:
     lines = doc.splitlines()
     desc_lines: List[str] = []
     params: Dict[str, str] = {}
-    in_args, indent, current = False, None, None
+    in_args, in_desc, indent, current = False, True, None, None
     for line in lines:
         if _ARGS_HEADER.match(line):
-            in_args = True
+            in_args, in_desc = True, False
             continue
         if not in_args:
-            desc_lines.append(line)
+            if _SECTION.match(line):  # Returns: / Raises: / ... - the description is what precedes the first section
+                in_desc = False
+            if in_desc:
+                desc_lines.append(line)
             continue
         if _SECTION.match(line) and (indent is None or len(line) - len(line.lstrip()) < indent):
             in_args = False
