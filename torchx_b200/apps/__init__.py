@@ -1,0 +1,1 @@
+"""Programs shipped with the launcher (see ``apps.utils``)."""

@@ -1,0 +1,1 @@
+"""Utility programs that run as (or around) a role's entrypoint."""

@@ -148,6 +148,15 @@ class RetryPolicy(str, Enum):
     ROLE = "ROLE"
 
 
+def _resolve_awaitable(pending: Any) -> Any:
+    """Drive ``pending`` to completion on a private event loop (attribute reads are synchronous)."""
+    loop = asyncio.new_event_loop()
+    try:
+        return loop.run_until_complete(pending)
+    finally:
+        loop.close()
+
+
 @dataclass
 class Role:
     """A homogeneous group of replicas (for ``dist.ddp``: the "nodes", each running ``nproc_per_node`` workers)."""
@@ -179,7 +188,7 @@ class Role:
                 lazy = None
             if lazy and attrname in lazy:
                 pending = lazy[attrname]
-                value = asyncio.get_event_loop().run_until_complete(pending) if inspect.isawaitable(pending) else pending()
+                value = _resolve_awaitable(pending) if inspect.isawaitable(pending) else pending()
                 object.__setattr__(self, attrname, value)
                 lazy[attrname] = lambda: value
         return get(attrname)
