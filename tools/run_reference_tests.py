@@ -86,16 +86,11 @@ PATCHES = [  # (regex, replacement) applied to every copied test file
      "    c.read_string(text)\n    return [_m.EntryPoint(n, v, g) for g in c.sections() for n, v in c.items(g)]"),
     (r"from torchx\.test\.fixtures import TestWithTmpDir", FIXTURE),
     (r"from torchx\.specs import named_resources, named_resources_aws, resource", "from torchx.specs import named_resources, resource\nnamed_resources_aws = None"),
-    (r"    TORCHX_HOME,\n    Workspace,\n\)", "    TORCHX_HOME,\n)\nWorkspace = None"),
-    (r"    UnknownAppException,\n    Workspace,\n\)", "    UnknownAppException,\n)\nWorkspace = None"),
-    (r"from torchx\.specs import AppDef, AppDryRunInfo, CfgVal, runopts, Workspace", "from torchx.specs import AppDef, AppDryRunInfo, CfgVal, runopts\nWorkspace = None"),
     (r"from torchx\.tracker\.api import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID", "from torchx.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID"),
     (r"from torchx\.workspace import WorkspaceMixin", "class WorkspaceMixin: pass"),
     (r"from torchx\.components\.component_test_base import ComponentTestCase", "import unittest\nclass ComponentTestCase(unittest.TestCase):\n    def validate(self, module, name):\n        pass"),
     (r"torchx\.util\.test\.entrypoints_test", "ref_entrypoints_test"),  # the test names ITSELF as an entry-point target
     (r"from \.test_util import write_shell_script", "import os as _o\ndef write_shell_script(dir, name, content):\n    p = _o.path.join(dir, name)\n    with open(p, 'w') as f:\n        f.write('#!/bin/bash\\n')\n        for l in content: f.write(l + '\\n')\n    _o.chmod(p, 0o755)\n    return p"),
-    (r"from torchx\.specs\.builders import \(\n    _create_args_parser,\n    BindMount,\n    component_args_from_str,\n    ComponentArgs,\n    DeviceMount,\n    make_app_handle,\n    materialize_appdef,\n    parse_mounts,\n    VolumeMount,\n\)",
-     "from torchx.specs.builders import _create_args_parser, component_args_from_str, ComponentArgs, materialize_appdef\nfrom torchx.specs.api import make_app_handle\nBindMount = DeviceMount = VolumeMount = parse_mounts = None"),
 ]
 
 FILES = [

@@ -114,15 +114,13 @@ def ddp(
         rdzv_port: c10d store port on rank 0's host; multi-node only (a single node uses a random free port)
         rdzv_backend: torchrun rendezvous backend; multi-node only
         rdzv_conf: extra rendezvous settings, e.g. join_timeout=600,timeout=600
-        mounts: container mounts; rejected here (no containers on the single-box path)
+        mounts: (container schedulers only) e.g. type=bind,src=/host,dst=/job[,readonly]; recorded in the Role, not acted on
+            by the local schedulers
         debug: apply the debug environment preset
         tee: which worker streams torchrun also copies to the console: 0 none, 1 stdout, 2 stderr, 3 both
     """
     if (script is None) == (m is None):
         raise ValueError("exactly one of --script and -m must be specified")
-    if mounts:
-        raise ValueError("mounts are a container feature; the single-box launch path has none (SURVEY.md §2 row 16)")
-
     min_nnodes, max_nnodes, nproc_per_node, nnodes_rep = parse_nnodes(j)
     if max_nnodes == 1:
         rdzv_endpoint: str = "localhost:0"  # single agent: let it pick any free port
@@ -159,7 +157,7 @@ def ddp(
         env=env,
         port_map={"c10d": rdzv_port},
         max_retries=max_retries,
-        mounts=[],
+        mounts=specs.parse_mounts(mounts) if mounts else [],
     )
     return specs.AppDef(name=argname.run_name, roles=[role], metadata=dict(metadata or {}))
 
@@ -193,7 +191,7 @@ def spmd(
         env: extra environment, e.g. A=1,B=2
         metadata: scheduler metadata, e.g. K1=v1,K2=v2
         max_retries: scheduler-level retries
-        mounts: rejected (no containers on the single-box path)
+        mounts: as for ``ddp``
         debug: apply the debug environment preset
     """
     return ddp(*args, script=script, m=m, image=image, name=name, h=h, j=str(StructuredJArgument.parse_from(h, j)),

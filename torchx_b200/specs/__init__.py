@@ -14,7 +14,9 @@ from .api import (  # noqa: F401
     AppState,
     AppStatus,
     AppStatusError,
+    BindMount,
     CfgVal,
+    DeviceMount,
     InvalidRunConfigException,
     MalformedAppHandleException,
     ParsedAppHandle,
@@ -26,6 +28,8 @@ from .api import (  # noqa: F401
     RoleStatus,
     UnknownAppException,
     UnknownSchedulerException,
+    VolumeMount,
+    Workspace,
     cases,
     get_type_name,
     is_started,
@@ -36,6 +40,7 @@ from .api import (  # noqa: F401
     runopt,
     runopts,
 )
+from .builders import materialize_appdef, parse_mounts  # noqa: F401,E402
 from .named_resources_generic import NAMED_RESOURCES as _GENERIC
 
 GiB: int = 1024

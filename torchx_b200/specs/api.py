@@ -3,7 +3,8 @@
 Same public names and semantics as reference torchx/specs/api.py (Resource:98, macros:183, RetryPolicy:277, Role:415,
 AppDef:505, AppState:525, AppStatus:628, AppDryRunInfo:784, runopt:835, runopts:885, parse_app_handle:1204) so that
 components, schedulers and the CLI written against TorchX keep working; the implementation is independent.
-Out of scope here (cloud / container only): mounts, Workspace syncing, fractional resources.
+Mounts and ``Workspace`` are part of the data model (AppDefs stay interchangeable with TorchX's) but only container /
+image-building schedulers act on them; the local schedulers of this package, like the reference's, do not.
 """
 from __future__ import annotations
 
@@ -15,6 +16,7 @@ import logging
 import os
 import pathlib
 import re
+import shutil
 import string
 from dataclasses import asdict, dataclass, field, fields
 from datetime import datetime
@@ -79,6 +81,83 @@ NULL_RESOURCE: Resource = Resource(cpu=-1, gpu=-1, memMB=-1)
 
 def _null_resource() -> Resource:
     return NULL_RESOURCE
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mounts / workspace: carried in the AppDef for container schedulers; the local schedulers do not act on them
+# ---------------------------------------------------------------------------------------------------------------
+@dataclass
+class BindMount:
+    """A host path made visible in the worker's container (reference specs/api.py:313-319)."""
+
+    src_path: str
+    dst_path: str
+    read_only: bool = False
+
+
+@dataclass
+class VolumeMount:
+    """A named persistent volume mounted at ``dst_path``."""
+
+    src: str
+    dst_path: str
+    read_only: bool = False
+
+
+@dataclass
+class DeviceMount:
+    """A host device node; ``permissions`` is a subset of ``rwm`` (read, write, mknod)."""
+
+    src_path: str
+    dst_path: str
+    permissions: str = "rwm"
+
+
+@dataclass
+class Workspace:
+    """``{local path: sub-directory in the job's image}`` - what an image-building scheduler copies before launch
+    (reference specs/api.py:340-411).  An empty sub-directory means "into the image root"."""
+
+    projects: Dict[str, str]
+
+    def __bool__(self) -> bool:
+        return bool(self.projects)
+
+    def __eq__(self, other: object) -> bool:
+        return isinstance(other, Workspace) and self.projects == other.projects
+
+    def __hash__(self) -> int:
+        return hash(frozenset(self.projects.items()))
+
+    def is_unmapped_single_project(self) -> bool:
+        """One project, copied to the image root."""
+        return len(self.projects) == 1 and not next(iter(self.projects.values()))
+
+    def merge_into(self, outdir: Union[str, "os.PathLike[str]"]) -> None:
+        """Materialise the mapping under ``outdir`` (files copied, directories merged)."""
+        for src, sub in self.projects.items():
+            dst = pathlib.Path(outdir) / sub
+            if pathlib.Path(src).is_file():
+                shutil.copy2(src, dst)
+            else:
+                shutil.copytree(src, dst, dirs_exist_ok=True)
+
+    @staticmethod
+    def from_str(workspace: Optional[str]) -> "Workspace":
+        """``"/one/dir"`` or a YAML mapping ``{"/a": "sub", "/b": null}`` (null = image root); empty -> no projects."""
+        if not workspace:
+            return Workspace({})
+        import yaml
+
+        parsed = yaml.safe_load(workspace)
+        if isinstance(parsed, str):
+            return Workspace({parsed: ""})
+        return Workspace({k: (v or "") for k, v in parsed.items()})
+
+    def __str__(self) -> str:  # for log lines; from_str() does not read this format back
+        if self.is_unmapped_single_project():
+            return next(iter(self.projects))
+        return ";".join(f"{k}:{v}" if v else k for k, v in self.projects.items())
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -173,8 +252,8 @@ class Role:
     resource: Resource = field(default_factory=_null_resource)
     port_map: Dict[str, int] = field(default_factory=dict)
     metadata: Dict[str, Any] = field(default_factory=dict)
-    mounts: List[Any] = field(default_factory=list)
-    workspace: Optional[Any] = None
+    mounts: List[Union[BindMount, VolumeMount, DeviceMount]] = field(default_factory=list)
+    workspace: Optional[Workspace] = None
     # Deprecated in TorchX but still honoured: {attribute name: zero-arg callable | awaitable} evaluated on first read
     # of that attribute, then cached (reference api.py:469-487).
     overrides: Dict[str, Any] = field(default_factory=dict)

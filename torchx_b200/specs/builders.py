@@ -10,12 +10,14 @@ from __future__ import annotations
 
 import argparse
 import inspect
+import os
 import re
 import typing
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Mapping, Optional, Tuple
+from enum import Enum
+from typing import Any, Callable, Dict, List, Mapping, Optional, Tuple, Union
 
-from torchx_b200.specs.api import AppDef
+from torchx_b200.specs.api import AppDef, BindMount, DeviceMount, VolumeMount, make_app_handle  # noqa: F401
 from torchx_b200.util.types import decode, decode_optional, get_argparse_param_type, is_bool
 
 _ARGS_HEADER = re.compile(r"^\s*(Args|Arguments|Parameters)\s*:\s*$")
@@ -142,3 +144,51 @@ def materialize_appdef(cmpnt_fn: Callable[..., AppDef], cmpnt_args: List[str], c
     if not isinstance(app, AppDef):
         raise TypeError(f"Expected a component that returns `AppDef`, but got `{type(app)}`")
     return app
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mounts
+# ---------------------------------------------------------------------------------------------------------------
+class MountType(str, Enum):
+    BIND = "bind"
+    VOLUME = "volume"
+    DEVICE = "device"
+
+
+# accepted spellings -> canonical option name (docker's --mount vocabulary)
+_MOUNT_OPT_MAP: Mapping[str, str] = {"type": "type", "src": "src", "source": "src", "dst": "dst", "destination": "dst", "target": "dst",
+                                     "readonly": "readonly", "read_only": "readonly", "perm": "perm"}
+
+
+def parse_mounts(opts: List[str]) -> List[Union[BindMount, VolumeMount, DeviceMount]]:
+    """``["type=bind", "src=/host", "dst=/job", "readonly", "type=device", "src=/dev/infiniband"]`` -> typed mounts
+    (reference specs/builders.py:311-376).  Every mount starts with its ``type=``; a device's ``dst`` defaults to its
+    ``src`` and its ``perm`` to ``rwm``; a leading ``~`` in a bind source is expanded."""
+    groups: List[Dict[str, str]] = []
+    for opt in opts:
+        key, _, val = opt.partition("=")
+        if key not in _MOUNT_OPT_MAP:
+            raise KeyError(f"unknown mount option {key}, must be one of {list(_MOUNT_OPT_MAP.keys())}")
+        key = _MOUNT_OPT_MAP[key]
+        if key == "type":
+            groups.append({})
+        elif not groups:
+            raise KeyError("type must be specified first")
+        groups[-1][key] = val
+    mounts: List[Union[BindMount, VolumeMount, DeviceMount]] = []
+    for g in groups:
+        kind = g.get("type")
+        if kind == MountType.BIND:
+            src = os.path.expanduser(g["src"]) if g["src"].startswith("~") else g["src"]
+            mounts.append(BindMount(src_path=src, dst_path=g["dst"], read_only="readonly" in g))
+        elif kind == MountType.VOLUME:
+            mounts.append(VolumeMount(src=g["src"], dst_path=g["dst"], read_only="readonly" in g))
+        elif kind == MountType.DEVICE:
+            perm = g.get("perm", "rwm")
+            wrong = [c for c in perm if c not in "rwm"]
+            if wrong:
+                raise ValueError(f"{wrong[0]} is not a valid permission flags must one of r,w,m")
+            mounts.append(DeviceMount(src_path=g["src"], dst_path=g.get("dst", g["src"]), permissions=perm))
+        else:
+            raise ValueError(f"invalid mount type {kind!r}, must be one of {[m.value for m in MountType]}")
+    return mounts
