@@ -88,7 +88,6 @@ PATCHES = [  # (regex, replacement) applied to every copied test file
     (r"from torchx\.specs import named_resources, named_resources_aws, resource", "from torchx.specs import named_resources, resource\nnamed_resources_aws = None"),
     (r"from torchx\.tracker\.api import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID", "from torchx.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID"),
     (r"from torchx\.workspace import WorkspaceMixin", "class WorkspaceMixin: pass"),
-    (r"from torchx\.components\.component_test_base import ComponentTestCase", "import unittest\nclass ComponentTestCase(unittest.TestCase):\n    def validate(self, module, name):\n        pass"),
     (r"torchx\.util\.test\.entrypoints_test", "ref_entrypoints_test"),  # the test names ITSELF as an entry-point target
     (r"from \.test_util import write_shell_script", "import os as _o\ndef write_shell_script(dir, name, content):\n    p = _o.path.join(dir, name)\n    with open(p, 'w') as f:\n        f.write('#!/bin/bash\\n')\n        for l in content: f.write(l + '\\n')\n    _o.chmod(p, 0o755)\n    return p"),
 ]
@@ -102,7 +101,8 @@ FILES = [
     "cli/test/cmd_run_test.py", "cli/test/cmd_log_test.py", "cli/test/cmd_status_test.py", "cli/test/cmd_describe_test.py",
     "cli/test/cmd_cancel_test.py", "cli/test/cmd_list_test.py", "cli/test/cmd_runopts_test.py", "cli/test/cmd_configure_test.py",
     "cli/test/main_test.py", "cli/test/argparse_util_test.py", "plugins/test/register_test.py", "plugins/test/registry_test.py",
-    "util/test/entrypoints_test.py",
+    "util/test/entrypoints_test.py", "util/test/cuda_test.py", "util/test/modules_test.py", "util/test/shlex_test.py", "util/test/strings_test.py",
+    "cli/test/cmd_delete_test.py", "components/test/utils_test.py", "apps/utils/test/copy_test.py",
 ]
 ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]
 if ONLY:

@@ -87,3 +87,36 @@ def python(*args: str, m: Optional[str] = None, c: Optional[str] = None, script:
     return specs.AppDef(name=name, roles=[specs.Role(name="python", image=image, entrypoint="python", num_replicas=num_replicas,
                                                     resource=specs.resource(cpu=cpu, gpu=gpu, memMB=memMB, h=h),
                                                     args=[*cmd, *args], env={"HYDRA_MAIN_MODULE": m} if m else {})])
+
+
+def binary(*args: str, entrypoint: str, name: str = "torchx_utils_binary", num_replicas: int = 1, cpu: int = 1, gpu: int = 0,
+           memMB: int = 1024, h: Optional[str] = None) -> specs.AppDef:
+    """
+    Runs an arbitrary executable with ``args`` - no shell, no interpreter (``torchx run utils.binary --entrypoint nvidia-smi -- -L``).
+
+    Args:
+        args: argv[1:] of the program
+        entrypoint: the executable (on PATH, or a path)
+        name: job name
+        num_replicas: how many copies to start
+        cpu: cores requested per replica
+        gpu: GPUs requested per replica
+        memMB: host memory requested per replica, MB
+        h: named resource; wins over cpu / gpu / memMB when given
+    """
+    return specs.AppDef(name=name, roles=[specs.Role(name="binary", image=specs.NONE, entrypoint=entrypoint, args=list(args),
+                                                    num_replicas=num_replicas, resource=specs.resource(cpu=cpu, gpu=gpu, memMB=memMB, h=h))])
+
+
+def copy(src: str, dst: str, image: str = torchx_b200.IMAGE) -> specs.AppDef:
+    """
+    Copies one file between two fsspec locations (local paths, ``s3://``, ``memory://`` ...); no directories.
+
+    Args:
+        src: where to read the file
+        dst: where to write it
+        image: recorded in the AppDef; the local schedulers run from the cwd
+    """
+    return specs.AppDef(name="torchx-utils-copy", roles=[specs.Role(
+        name="torchx-utils-copy", image=image, entrypoint="python", args=["-m", "torchx_b200.apps.utils.copy_main", "--src", src, "--dst", dst],
+        resource=specs.Resource(cpu=1, gpu=0, memMB=1024))])

@@ -20,6 +20,8 @@ from typing import Any, Iterator, Optional
 import torch
 import torch.distributed as dist
 
+from torchx_b200.util.cuda import has_cuda_devices
+
 _COMM: Optional[Any] = None  # torchx_b200.ddp.Communicator when init_pg("b200") was used
 
 
@@ -60,7 +62,7 @@ def local_device() -> torch.device:
         return torch.device("cuda", _COMM.device)
     if dist.is_available() and dist.is_initialized():
         return local_cuda_device() if dist.get_backend() == "nccl" else torch.device("cpu")
-    return torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+    return torch.device("cuda") if has_cuda_devices() else torch.device("cpu")
 
 
 def is_rank0() -> bool:
