@@ -120,7 +120,7 @@ def test_component_args_from_signature_and_docstring():
 
 
 def test_finder_builtin_file_and_module_forms(tmp_path):
-    assert list(get_builtin_components()) == ["dist.ddp", "dist.spmd", "utils.echo", "utils.python", "utils.sh", "utils.touch"]
+    assert sorted(get_builtin_components()) == ["dist.ddp", "dist.spmd", "utils.binary", "utils.copy", "utils.echo", "utils.python", "utils.sh", "utils.touch"]
     assert get_component("dist.ddp").fn.__name__ == "ddp"
     f = tmp_path / "comp.py"
     f.write_text(textwrap.dedent('''
