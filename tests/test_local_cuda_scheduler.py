@@ -200,12 +200,39 @@ def test_status_list_and_logs_resolve_from_another_process(tmp_path, monkeypatch
             assert sorted(b.log_iter(app_id, "env_worker", 0, streams=Stream.STDOUT)) == ["[0]:hello from rank 0 attempt 0\n", "[1]:hello from rank 1 attempt 0\n"]
             assert [(r.app_id, r.state) for r in b.list()] == [(app_id, AppState.SUCCEEDED)]
             assert b.describe("never-launched") is None
-            with pytest.raises(RuntimeError, match="another process"):
-                b._cancel_existing(app_id)
+            b.cancel(app_id)  # already terminal: a no-op, also from here
+            assert b.describe(app_id).state == AppState.SUCCEEDED
         finally:
             b.close()
         assert create_scheduler("other_session").list() == []
     finally:
+        a.close()
+
+
+def test_cancel_from_another_process_goes_through_the_registry(tmp_path, monkeypatch):
+    """`torchx cancel local_cuda://...` typed in a second shell: the request file is picked up by the launcher's supervisor
+    thread, which takes the gang down and records CANCELLED (the reference's local scheduler cannot do this:
+    local_scheduler.py:1099-1102 knows only the apps of its own process)."""
+    monkeypatch.setenv("TORCHX_HOME", str(tmp_path / "home"))
+    out = tmp_path / "out"
+    out.mkdir()
+    a, b = create_scheduler("sess"), create_scheduler("sess")  # launcher / the other process
+    try:
+        with mock.patch.object(a, "_cuda_device_count", return_value=0):
+            app_id = a.submit(ddp(str(out), "sleep", script=WORKER, j="1x2"), {"log_dir": str(tmp_path / "logs")})
+        time.sleep(1.0)
+        pids = [r.proc.pid for r in a._apps[app_id].replicas()]
+        assert b.describe(app_id).state == AppState.RUNNING
+        b.cancel(app_id)  # returns once the launcher has acknowledged, i.e. the workers are gone
+        for pid in pids:
+            with pytest.raises(ProcessLookupError):
+                os.kill(pid, 0)
+        assert a.describe(app_id).state == AppState.CANCELLED and b.describe(app_id).state == AppState.CANCELLED
+        assert not os.path.exists(os.path.join(str(tmp_path / "home"), "apps", "sess", f"{app_id}.cancel"))
+        with pytest.raises(RuntimeError, match="not in this session's registry"):
+            b._cancel_existing("never-launched")
+    finally:
+        b.close()
         a.close()
 
 

@@ -22,8 +22,10 @@ torchx/components/dist.py:261-308) and replaces what ``local_cwd`` + ``torchrun`
     ``attempt_<n>/rank_<local_rank>/``; ``error.json`` / ``SUCCESS`` as before, so ``torchx log|status`` work unchanged.
 
   * app registry: every scheduled app leaves ``$TORCHX_HOME/apps/<session>/<app_id>.json`` (default ``~/.torchx_b200``) pointing
-    at its log tree, so ``torchx status | log | list`` also resolve from ANOTHER process (the reference's local scheduler
-    keeps state in the submitting process only and ``list()`` raises, local_scheduler.py:615,1099-1102).
+    at its log tree and, once finished, holding its final state, so ``torchx status | log | list`` also resolve from ANOTHER
+    process (the reference's local scheduler keeps state in the submitting process only and ``list()`` raises,
+    local_scheduler.py:615,1099-1102).  ``torchx cancel`` from another process drops ``<app_id>.cancel`` next to the entry; the
+    launcher's supervisor thread takes the gang down within its 0.1 s poll and removes the file as the acknowledgement.
 
 Roles whose command is not a torchrun line (e.g. ``utils.echo``) are launched exactly as ``local_cwd`` would.
 """
@@ -47,6 +49,7 @@ from torchx_b200.schedulers.api import DescribeAppResponse, ListAppResponse, Str
 from torchx_b200.schedulers.local_scheduler import (
     COMBINED_LOG,
     ENV_CUDA_VISIBLE_DEVICES,
+    KILL_GRACE_S,
     NA,
     STDERR_LOG,
     STDOUT_LOG,
@@ -344,6 +347,10 @@ def registry_dir(session_name: str) -> str:
     return os.path.join(home, "apps", session_name or "default")
 
 
+def _cancel_request_path(session_name: str, app_id: str) -> str:
+    return os.path.join(registry_dir(session_name), f"{app_id}.cancel")
+
+
 def _pid_alive(pid: int) -> bool:
     try:
         os.kill(pid, 0)
@@ -374,6 +381,8 @@ class _AppRecord:
         m = self.manifest()
         if m is not None:
             return AppState[m.get("final_state", "UNKNOWN")], int(m.get("num_restarts", 0))
+        if "final_state" in self.entry:  # the supervisor's own record; outlives a temporary log dir
+            return AppState[self.entry["final_state"]], int(self.entry.get("num_restarts", 0))
         if _pid_alive(int(self.entry.get("launcher_pid", -1))):
             return AppState.RUNNING, 0
         return AppState.UNKNOWN, 0  # launcher gone without closing the app (killed -9): nothing supervises it any more
@@ -601,8 +610,11 @@ class LocalCudaScheduler(LocalScheduler):
         try:
             d = registry_dir(self.session_name)
             os.makedirs(d, exist_ok=True)
-            entry = {"app_id": app.id, "log_dir": app.log_dir, "launcher_pid": os.getpid(), "created": time.time(),
+            entry = {"app_id": app.id, "log_dir": app.log_dir, "launcher_pid": os.getpid(), "created": getattr(app, "created", None) or time.time(),
                      "scheduler": self.backend, "roles": {r: len(g) for r, g in app.request.groups.items()}}
+            app.created = entry["created"]
+            if is_terminal(app.state):
+                entry.update(final_state=app.state.name, num_restarts=app.num_restarts, finished=time.time())
             tmp = os.path.join(d, f".{app.id}.tmp")
             with open(tmp, "w") as f:
                 json.dump(entry, f)
@@ -634,12 +646,31 @@ class LocalCudaScheduler(LocalScheduler):
 
     # -- supervision --------------------------------------------------------------------------------------------------
     def _monitor(self, app: _CudaApp) -> None:
+        try:
+            self._supervise(app)
+        finally:
+            with app.lock:
+                if is_terminal(app.state):  # keep the outcome where `torchx list/status` of other processes find it even
+                    self._register(app)     # after a temporary log dir (and its SUCCESS manifest) is gone
+
+    def _supervise(self, app: _CudaApp) -> None:
         """Gang supervision: any worker failure kills the attempt; with retries left the whole gang is re-launched
         under the next epoch (RetryPolicy.APPLICATION semantics), otherwise the app is FAILED."""
         req = app.request
         while not app.stop_monitor.wait(MONITOR_POLL_S):
             with app.lock:
                 if is_terminal(app.state):
+                    return
+                # -- `torchx cancel` from another process: a request file next to the registry entry ------------------
+                cancel_request = _cancel_request_path(self.session_name, app.id)
+                if os.path.exists(cancel_request):
+                    app.failure_msg = "cancelled on request of another process"
+                    app.set_state(AppState.CANCELLED)
+                    app.close()  # SIGTERM, grace period, SIGKILL; then the SUCCESS manifest other processes read the state from
+                    try:
+                        os.unlink(cancel_request)  # doubles as the acknowledgement the requester waits for
+                    except OSError:
+                        pass
                     return
                 # -- process_monitor semantics for the gang (reference torchx/apps/utils/process_monitor.py:65-118) --
                 timed_out = app.deadline is not None and time.monotonic() > app.deadline
@@ -685,7 +716,7 @@ class LocalCudaScheduler(LocalScheduler):
         app = self._apps.get(app_id)
         if app is None:
             rec = self._record(app_id)  # launched by another process?
-            if rec is None or not os.path.isdir(rec.log_dir):
+            if rec is None or not (os.path.isdir(rec.log_dir) or "final_state" in rec.entry):
                 return None
             state, restarts = rec.state()
             return DescribeAppResponse(app_id=app_id, state=state, num_restarts=restarts, structured_error_msg=NONE,
@@ -715,12 +746,39 @@ class LocalCudaScheduler(LocalScheduler):
     def _cancel_existing(self, app_id: str) -> None:
         app = self._apps.get(app_id)
         if app is None:
-            raise RuntimeError(f"app {app_id} was launched by another process; only its launcher can cancel it")
+            self._request_cancel(app_id)
+            return
         if isinstance(app, _CudaApp):
             app.stop_monitor.set()
         with app.lock:
             app.close()
             app.state = AppState.CANCELLED
+
+    def _request_cancel(self, app_id: str) -> None:
+        """Cancel an app another process launched: leave ``<registry>/<app_id>.cancel`` for its supervisor thread (which
+        polls every MONITOR_POLL_S) and wait until it has acknowledged by removing the file, i.e. the gang is down."""
+        rec = self._record(app_id)
+        if rec is None:
+            raise RuntimeError(f"app {app_id} is not in this session's registry")
+        state, _ = rec.state()
+        if is_terminal(state):
+            return
+        launcher = int(rec.entry.get("launcher_pid", -1))
+        if state == AppState.UNKNOWN or not _pid_alive(launcher):
+            raise RuntimeError(f"app {app_id}: its launcher (pid {launcher}) is gone, so nothing supervises the workers any more; "
+                               f"their pids are in the logs under {rec.log_dir}")
+        path = _cancel_request_path(self.session_name, app_id)
+        with open(path, "w") as f:
+            f.write(f"requested by pid {os.getpid()} at {time.time():.3f}\n")
+        deadline = time.monotonic() + KILL_GRACE_S + 5.0
+        while os.path.exists(path):
+            if time.monotonic() > deadline or not _pid_alive(launcher):
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
+                raise RuntimeError(f"app {app_id}: the launcher (pid {launcher}) did not act on the cancel request")
+            time.sleep(MONITOR_POLL_S)
 
     def close(self) -> None:
         for app in list(self._apps.values()):
