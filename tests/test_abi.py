@@ -26,6 +26,24 @@ def test_library_exports_every_declared_symbol():
     assert N.lib().b2_version() == N.B2_ABI_VERSION
 
 
+def test_plain_c_consumer_builds_against_the_header_and_resolves_every_symbol(tmp_path):
+    """The boundary is a C ABI: strict C99 (-pedantic, no C++), no torch anywhere - `gcc` + `dlopen` is all a host needs."""
+    import subprocess
+
+    N.build_library()
+    exe = tmp_path / "consumer"
+    syms = ", ".join(f'"{s}"' for s in _declared())
+    cmd = ["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", f"-I{os.path.join(ROOT, 'include')}", f"-DB2_CONSUMER_SYMBOLS={syms}",
+           os.path.join(ROOT, "tests", "abi", "consumer.c"), "-o", str(exe), "-ldl"]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    res = subprocess.run([str(exe), N.LIB_PATH], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.strip() == f"ok {len(_declared())} symbols abi {N.B2_ABI_VERSION}"
+    for binary in (str(exe), N.LIB_PATH):  # neither the consumer nor the library itself links torch or python (cudart is static)
+        ldd = subprocess.run(["ldd", binary], capture_output=True, text=True).stdout
+        assert "torch" not in ldd and "python" not in ldd, ldd
+
+
 def test_header_constants_match_binding():
     src = open(os.path.join(ROOT, "include", "b200ddp.h")).read()
     for name in ("B2_OK", "B2_EINVAL", "B2_ECUDA", "B2_ESYS", "B2_ETIMEOUT", "B2_ENOPEER", "B2_ESTATE", "B2_F32_WIRE_BF16",
