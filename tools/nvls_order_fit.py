@@ -51,6 +51,53 @@ def analyse(path):
     print()
 
 
+def structure(path):
+    """W = 2 only: what does the rounding decision depend on?  Same (a, b) at two positions; same sum at two positions; the
+    'tie' class (one input pair repeated at every position)."""
+    from collections import defaultdict
+
+    d = np.load(path)
+    if int(d["world"][0]) != 2:
+        return
+    names = [str(x) for x in d["class_names"]]
+    a, b = d["bf16_in"][0].astype(np.uint32), d["bf16_in"][1].astype(np.uint32)
+    out = (d["bf16_out_nvls"] if "bf16_out_nvls" in d.files else d["bf16_out"][0, 0]).astype(np.uint32)
+    with np.errstate(all="ignore"):
+        s64 = (a << 16).view(np.float32).astype(np.float64) + (b << 16).view(np.float32).astype(np.float64)
+        s32 = s64.astype(np.float32)
+    sb = s32.view(np.uint32)
+    rem, trunc = sb & 0xFFFF, sb >> 16
+    cls = np.zeros(a.size, dtype=int)
+    for i, (s0, ln) in enumerate(zip(d["class_start"], d["class_len"])):
+        cls[s0:s0 + ln] = i
+    inexact = np.isfinite(s64) & (s32.astype(np.float64) == s64) & (rem != 0) & ((out == trunc) | (out == trunc + 1))
+    pool = inexact & np.isin(cls, [names.index(c) for c in ("wide", "narrow", "subnormal")])
+    up = out == trunc + 1
+
+    def inconsistent(key):
+        groups = defaultdict(set)
+        for i in np.flatnonzero(pool):
+            groups[key(i)].add(bool(up[i]))
+        multi = [v for v in groups.values()]
+        sizes = defaultdict(int)
+        for i in np.flatnonzero(pool):
+            sizes[key(i)] += 1
+        multi = [k for k, c in sizes.items() if c > 1]
+        return sum(1 for k in multi if len(groups[k]) > 1), len(multi)
+
+    print(f"### what the decision depends on ({os.path.basename(path)}, inexact sums of the wide / narrow / subnormal classes: {int(pool.sum())})\n")
+    for label, key in (("same fp32 sum at several positions", lambda i: int(sb[i])),
+                       ("same fp32 sum and same lane (position mod 8)", lambda i: (int(sb[i]), int(i) % 8)),
+                       ("same input pair (a, b) at several positions", lambda i: (int(a[i]), int(b[i])))):
+        bad, tot = inconsistent(key)
+        print(f"* {label}: {tot} groups, {bad} of them rounded BOTH ways")
+    t = cls == names.index("tie")
+    print(f"* 'tie' class (the pair 1.0, 2^-8 at all {int(t.sum())} positions, remainder exactly 1/2): {int((out[t] == trunc[t] + 1).sum())} rounded up, "
+          f"{int((out[t] == trunc[t]).sum())} down; ties elsewhere: {float(up[pool & (rem == 0x8000)].mean()):.2f} rounded up\n")
+
+
 if __name__ == "__main__":
     for p in sys.argv[1:]:
         analyse(p)
+    for p in sys.argv[1:]:
+        structure(p)
