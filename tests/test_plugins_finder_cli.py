@@ -417,3 +417,39 @@ def test_local_rank_warns_when_group_is_up_without_launcher_env(monkeypatch):
     with mock.patch("torch.cuda.is_available", return_value=True), mock.patch("torch.cuda.device_count", return_value=0), \
             mock.patch("torchx_b200.distributed.dist.init_process_group") as init:
         assert d.init_pg("auto").type == "cpu" and init.call_args.kwargs["backend"] == "gloo"  # CUDA build of torch on a GPU-less host
+
+
+# ---- runner telemetry -------------------------------------------------------------------------------------------
+def test_runner_calls_are_recorded_as_events(tmp_path):
+    """Every Runner API call yields one TorchxEvent (reference torchx/runner/events): scheduler, app id, image, run config,
+    timings, and the exception when the call raised.  Nothing is emitted unless a handler is installed."""
+    import logging
+
+    from torchx_b200.runner import events, get_runner
+
+    seen = []
+
+    class Sink(logging.Handler):
+        def emit(self, record):
+            seen.append(events.TorchxEvent.deserialize(record.getMessage()))
+
+    old_handler, old_logger = events.handlers["null"], events._events_logger
+    events.handlers["null"], events._events_logger = Sink(), None
+    try:
+        with get_runner() as runner:
+            handle = runner.run_component("utils.echo", ["--msg", "x"], "local_cwd", cfg={"log_dir": str(tmp_path)})
+            runner.wait(handle, wait_interval=0.1)
+            with pytest.raises(specs.MalformedAppHandleException):
+                runner.status("not-a-handle")
+    finally:
+        events.handlers["null"], events._events_logger = old_handler, old_logger
+    by_api = {e.api: e for e in seen}
+    app_id = handle.rsplit("/", 1)[1]
+    assert {"dryrun", "schedule", "run_component", "wait", "status"} <= set(by_api)
+    assert by_api["schedule"].app_id == app_id and by_api["schedule"].scheduler == "local_cwd" and by_api["schedule"].app_image
+    assert json.loads(by_api["dryrun"].runcfg) == {"log_dir": str(tmp_path)}
+    failed = [e for e in seen if e.exception_type]
+    assert [e.exception_type for e in failed] == ["MalformedAppHandleException"] and "not-a-handle" in failed[0].exception_message
+    assert json.loads(failed[0].exception_source_location)["name"] == "parse_app_handle" and "Traceback" in failed[0].raw_exception
+    assert all(e.wall_time_usec >= 0 and e.cpu_time_usec >= 0 and e.session for e in seen)
+    assert events.TorchxEvent.deserialize(str(seen[0])) == seen[0]

@@ -102,7 +102,7 @@ FILES = [
     "cli/test/cmd_cancel_test.py", "cli/test/cmd_list_test.py", "cli/test/cmd_runopts_test.py", "cli/test/cmd_configure_test.py",
     "cli/test/main_test.py", "cli/test/argparse_util_test.py", "plugins/test/register_test.py", "plugins/test/registry_test.py",
     "util/test/entrypoints_test.py", "util/test/cuda_test.py", "util/test/modules_test.py", "util/test/shlex_test.py", "util/test/strings_test.py",
-    "cli/test/cmd_delete_test.py", "components/test/utils_test.py", "apps/utils/test/copy_test.py",
+    "cli/test/cmd_delete_test.py", "components/test/utils_test.py", "apps/utils/test/copy_test.py", "runner/events/test/lib_test.py",
 ]
 ONLY = [a for a in sys.argv[1:] if not a.startswith("-")]
 if ONLY:

@@ -4,10 +4,11 @@ Behaviour follows reference torchx/runner/api.py (Runner:90, run_component:159, 
 wait:493, cancel, describe, log_lines:557, list, _scheduler:621, get_runner:649): validates the AppDef, injects
 ``TORCHX_JOB_ID`` / ``TORCHX_INTERNAL_SESSION_ID`` into every role, resolves the scheduler cfg, dry-runs, schedules, polls.
 Scheduler factories receive ``TORCHX_*`` environment variables (lower-cased, prefix stripped) as keyword arguments.
-Tracker backends and the per-call telemetry events of the reference are out of scope.
+Tracker backends of the reference are out of scope; per-call telemetry events go to ``runner/events`` (a NullHandler by default).
 """
 from __future__ import annotations
 
+import json
 import logging
 import os
 import time
@@ -38,15 +39,45 @@ logger = logging.getLogger(__name__)
 
 
 def _logged(api: str):
-    """Wrap a Runner method in the (no-op by default) per-call event of runner/events."""
+    """Run a Runner method inside its telemetry event (runner/events): scheduler, app id, image, run config and workspace are
+    taken from the call's own arguments / result, as the reference fills them in by hand in each method
+    (torchx/runner/api.py:176-191, 388-440 ...)."""
 
     def deco(fn):
         import functools
+        import inspect
+
+        sig = inspect.signature(fn)
 
         @functools.wraps(fn)
         def wrapper(self, *args, **kwargs):
-            with events.log_event(api):
-                return fn(self, *args, **kwargs)
+            try:
+                bound = sig.bind_partial(self, *args, **kwargs).arguments
+            except TypeError:  # let the real call raise the proper error
+                bound = {}
+            scheduler, app_id, image = bound.get("scheduler"), None, None
+            handle = bound.get("app_handle")
+            if isinstance(handle, str):
+                try:
+                    scheduler, _, app_id = parse_app_handle(handle)
+                except Exception:  # noqa: BLE001 - a malformed handle is the wrapped method's business
+                    pass
+            info = bound.get("dryrun_info")
+            if info is not None:
+                scheduler = getattr(info, "_scheduler", None) or scheduler
+            app = bound.get("app") if bound.get("app") is not None else getattr(info, "_app", None)
+            if app is not None and getattr(app, "roles", None):
+                image = app.roles[0].image
+            cfg, workspace = bound.get("cfg"), bound.get("workspace")
+            with events.log_event(api, scheduler if isinstance(scheduler, str) else None, app_id, app_image=image,
+                                  runcfg=json.dumps(dict(cfg)) if cfg else None, workspace=str(workspace) if workspace else None) as ctx:
+                out = fn(self, *args, **kwargs)
+                if isinstance(out, str) and "://" in out:  # schedule / run / run_component return the new app's handle
+                    try:
+                        ctx._torchx_event.app_id = parse_app_handle(out)[2]
+                    except Exception:  # noqa: BLE001
+                        pass
+                return out
 
         return wrapper
 
