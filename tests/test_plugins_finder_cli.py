@@ -453,3 +453,23 @@ def test_runner_calls_are_recorded_as_events(tmp_path):
     assert json.loads(failed[0].exception_source_location)["name"] == "parse_app_handle" and "Traceback" in failed[0].raw_exception
     assert all(e.wall_time_usec >= 0 and e.cpu_time_usec >= 0 and e.session for e in seen)
     assert events.TorchxEvent.deserialize(str(seen[0])) == seen[0]
+
+
+def test_tracker_configuration_is_forwarded_to_the_workers(tmp_path, monkeypatch):
+    """.torchxconfig [torchx:tracker] / [tracker:<name>] (or the TORCHX_TRACKERS* variables) end up in every role's environment
+    (reference torchx/runner/api.py:68-87, 386-391); the backends themselves live in the worker."""
+    from torchx_b200.runner import get_runner
+    from torchx_b200.runner.api import get_configured_trackers
+
+    (tmp_path / ".torchxconfig").write_text("[torchx:tracker]\nfsspec =\nmlflow =\n\n[tracker:fsspec]\nconfig = /tmp/tracker/root\n")
+    monkeypatch.setenv("TORCHXCONFIG", str(tmp_path / ".torchxconfig"))
+    monkeypatch.delenv("TORCHX_TRACKERS", raising=False)
+    assert get_configured_trackers() == {"fsspec": "/tmp/tracker/root", "mlflow": None}
+    with get_runner() as runner:
+        info = runner.dryrun_component("dist.ddp", ["-j", "1x2", "--script", "t.py"], "local_cuda", parent_run_id="exp7")
+    env = info._app.roles[0].env
+    assert env["TORCHX_TRACKERS"] == "fsspec,mlflow" and env["TORCHX_TRACKER_FSSPEC_CONFIG"] == "/tmp/tracker/root"
+    assert "TORCHX_TRACKER_MLFLOW_CONFIG" not in env and env["TORCHX_PARENT_RUN_ID"] == "exp7"
+    monkeypatch.setenv("TORCHX_TRACKERS", "only")
+    monkeypatch.setenv("TORCHX_TRACKER_ONLY_CONFIG", "s3://bucket/cfg")
+    assert get_configured_trackers() == {"only": "s3://bucket/cfg"}

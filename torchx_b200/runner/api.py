@@ -18,7 +18,14 @@ from typing import Any, Dict, Iterable, List, Mapping, Optional, Tuple, Union
 from torchx_b200.runner import events
 from torchx_b200.schedulers import SchedulerFactory, get_scheduler_factories
 from torchx_b200.schedulers.api import ListAppResponse, Scheduler, Stream
-from torchx_b200.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID, TORCHX_INTERNAL_SESSION_ID
+from torchx_b200.runner import config
+from torchx_b200.settings import (
+    ENV_TORCHX_JOB_ID,
+    ENV_TORCHX_PARENT_RUN_ID,
+    ENV_TORCHX_TRACKERS,
+    TORCHX_INTERNAL_SESSION_ID,
+    tracker_config_env_var_name,
+)
 from torchx_b200.specs.api import (
     AppDef,
     AppDryRunInfo,
@@ -36,6 +43,26 @@ from torchx_b200.specs.finder import get_component
 from torchx_b200.util.session import get_session_id_or_create_new
 
 logger = logging.getLogger(__name__)
+
+
+def get_configured_trackers() -> Dict[str, Optional[str]]:
+    """``{tracker name: its config string}`` for the job being submitted: names from ``[torchx:tracker]`` in .torchxconfig
+    (or ``$TORCHX_TRACKERS``, which replaces the list), each one's config from ``[tracker:<name>] config = ...`` (or
+    ``$TORCHX_TRACKER_<NAME>_CONFIG``).  The Runner only FORWARDS this to the workers' environment; tracker backends
+    themselves run in the worker process and are not part of this package (reference torchx/runner/api.py:68-87)."""
+    names = list(config.get_configs(prefix="torchx", name="tracker").keys())
+    if ENV_TORCHX_TRACKERS in os.environ:
+        names = [n for n in os.environ[ENV_TORCHX_TRACKERS].split(",") if n]
+        logger.info(f"Using {ENV_TORCHX_TRACKERS}={names} as tracker names")
+    configured: Dict[str, Optional[str]] = {}
+    for name in names:
+        value = config.get_config(prefix="tracker", name=name, key="config")
+        env_name = tracker_config_env_var_name(name)
+        if env_name in os.environ:
+            value = os.environ[env_name]
+            logger.info(f"Using {env_name}={value} for `{name}` tracker")
+        configured[name] = value
+    return configured
 
 
 def _logged(api: str):
@@ -166,6 +193,7 @@ class Runner:
             # WorkspaceMixin schedulers only); the local ones run from the cwd, so like the reference it is ignored.
             logger.debug("workspace `%s` ignored: `%s` runs from the current directory", workspace, scheduler)
         parent_run_id = os.environ.get(ENV_TORCHX_PARENT_RUN_ID, parent_run_id)
+        trackers = get_configured_trackers()
         for role in app.roles:
             if not role.entrypoint:
                 raise ValueError(f"No entrypoint for role: {role.name}. Did you forget to call role.runs(entrypoint, args, env)?")
@@ -175,6 +203,11 @@ class Runner:
             role.env[TORCHX_INTERNAL_SESSION_ID] = get_session_id_or_create_new()
             if parent_run_id:
                 role.env[ENV_TORCHX_PARENT_RUN_ID] = parent_run_id
+            if trackers:
+                role.env[ENV_TORCHX_TRACKERS] = ",".join(trackers)
+            for tracker_name, tracker_config in trackers.items():
+                if tracker_config:
+                    role.env[tracker_config_env_var_name(tracker_name)] = tracker_config
         sched = self._scheduler(scheduler)
         resolved = sched.run_opts().resolve(cfg or {})
         sched._pre_build_validate(app, scheduler, resolved)

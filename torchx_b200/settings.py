@@ -8,3 +8,9 @@ ENV_TORCHX_IMAGE = "TORCHX_IMAGE"
 ENV_TORCHXCONFIG = "TORCHXCONFIG"
 TORCHX_INTERNAL_SESSION_ID = "TORCHX_INTERNAL_SESSION_ID"
 TORCHX_HOME = "TORCHX_HOME"
+
+
+def tracker_config_env_var_name(tracker_name: str) -> str:
+    """``TORCHX_TRACKER_<NAME>_CONFIG``: where a worker-side tracker backend finds its configuration
+    (reference torchx/tracker/api.py:125-127)."""
+    return f"TORCHX_TRACKER_{tracker_name.upper()}_CONFIG"
