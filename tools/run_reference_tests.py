@@ -79,7 +79,6 @@ class DistributedTestCase(TestWithTmpDir):
 
 PATCHES = [  # (regex, replacement) applied to every copied test file
     (r"from torchx\.test\.fixtures import DistributedTestCase, IS_CI, IS_MACOS", DIST_FIXTURE),
-    (r"from torchx\.workspace\.api import WorkspaceMixin", "import typing as _t\nclass WorkspaceMixin(_t.Generic[_t.TypeVar('T')]):\n    pass"),
     (r"from torchx\.runtime\.tracking import FsspecResultTracker", "FsspecResultTracker = None"),
     (r"from torchx\.util\.test\.entrypoints_test import EntryPoint_from_text",
      "def EntryPoint_from_text(text):\n    import configparser, importlib.metadata as _m\n    c = configparser.ConfigParser(delimiters='=')\n"
@@ -87,7 +86,6 @@ PATCHES = [  # (regex, replacement) applied to every copied test file
     (r"from torchx\.test\.fixtures import TestWithTmpDir", FIXTURE),
     (r"from torchx\.specs import named_resources, named_resources_aws, resource", "from torchx.specs import named_resources, resource\nnamed_resources_aws = None"),
     (r"from torchx\.tracker\.api import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID", "from torchx.settings import ENV_TORCHX_JOB_ID, ENV_TORCHX_PARENT_RUN_ID"),
-    (r"from torchx\.workspace import WorkspaceMixin", "class WorkspaceMixin: pass"),
     (r"torchx\.util\.test\.entrypoints_test", "ref_entrypoints_test"),  # the test names ITSELF as an entry-point target
     (r"from \.test_util import write_shell_script", "import os as _o\ndef write_shell_script(dir, name, content):\n    p = _o.path.join(dir, name)\n    with open(p, 'w') as f:\n        f.write('#!/bin/bash\\n')\n        for l in content: f.write(l + '\\n')\n    _o.chmod(p, 0o755)\n    return p"),
 ]

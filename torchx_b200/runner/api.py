@@ -40,7 +40,9 @@ from torchx_b200.specs.api import (
 )
 from torchx_b200.specs.builders import materialize_appdef
 from torchx_b200.specs.finder import get_component
+from torchx_b200.specs.api import Workspace
 from torchx_b200.util.session import get_session_id_or_create_new
+from torchx_b200.workspace.api import WorkspaceMixin
 
 logger = logging.getLogger(__name__)
 
@@ -188,10 +190,6 @@ class Runner:
                parent_run_id: Optional[str] = None) -> AppDryRunInfo:
         if not app.roles:
             raise ValueError(f"No roles for app: {app.name}. Did you forget to add roles to AppDef?")
-        if workspace:
-            # Only image-building schedulers consume a workspace (reference runner/api.py:405-424 applies it to
-            # WorkspaceMixin schedulers only); the local ones run from the cwd, so like the reference it is ignored.
-            logger.debug("workspace `%s` ignored: `%s` runs from the current directory", workspace, scheduler)
         parent_run_id = os.environ.get(ENV_TORCHX_PARENT_RUN_ID, parent_run_id)
         trackers = get_configured_trackers()
         for role in app.roles:
@@ -211,6 +209,14 @@ class Runner:
         sched = self._scheduler(scheduler)
         resolved = sched.run_opts().resolve(cfg or {})
         sched._pre_build_validate(app, scheduler, resolved)
+        if isinstance(sched, WorkspaceMixin):
+            # only image-building (plugin) schedulers consume a workspace (reference runner/api.py:405-424); the argument wins
+            # over roles[0].workspace for backwards compatibility.  The local schedulers run from the cwd and ignore it.
+            if workspace:
+                app.roles[0].workspace = Workspace.from_str(workspace) if isinstance(workspace, str) else workspace
+            sched.build_workspaces(app.roles, resolved)
+        elif workspace:
+            logger.debug("workspace `%s` ignored: `%s` runs from the current directory", workspace, scheduler)
         sched._validate(app, scheduler, resolved)
         info = sched.submit_dryrun(app, resolved)
         info._scheduler = scheduler

@@ -215,8 +215,15 @@ class Scheduler(abc.ABC, Generic[T]):
 
     # -- submission -------------------------------------------------------------------------------------------------
     def submit(self, app: AppDef, cfg: T, workspace: Optional[Any] = None) -> str:
+        """Submit directly (the Runner is the production route).  ``workspace`` is only meaningful for schedulers that mix in
+        ``WorkspaceMixin`` (reference schedulers/api.py:383-403); it becomes ``roles[0].workspace`` and is built first."""
         if workspace:
-            raise NotImplementedError("workspaces are not supported on the single-box launch path (cwd is the image)")
+            from torchx_b200.specs.api import Workspace
+            from torchx_b200.workspace.api import WorkspaceMixin
+
+            assert isinstance(self, WorkspaceMixin), f"{type(self).__name__} does not build workspaces"
+            app.roles[0].workspace = Workspace.from_str(workspace) if isinstance(workspace, str) else workspace
+            self.build_workspaces(app.roles, self.run_opts().resolve(cfg))  # type: ignore[arg-type]
         return self.schedule(self.submit_dryrun(app, cfg))
 
     def submit_dryrun(self, app: AppDef, cfg: T) -> AppDryRunInfo:
