@@ -97,6 +97,9 @@ def structure(path):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) < 2 or sys.argv[1] in ("-h", "--help"):
+        print(__doc__)
+        sys.exit(0)
     for p in sys.argv[1:]:
         analyse(p)
     for p in sys.argv[1:]:

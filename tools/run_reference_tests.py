@@ -129,6 +129,11 @@ def _rename_plugin_namespace(root: str) -> None:
 
 
 def main() -> None:
+    if "-h" in sys.argv or "--help" in sys.argv:
+        print(__doc__)
+        print("    python tools/run_reference_tests.py cli/ plugins/     # only files whose path contains one of the words")
+        print("    python tools/run_reference_tests.py --keep ...        # leave the prepared directory behind (path printed)")
+        return
     if not os.path.isdir(REF):
         raise SystemExit(f"{REF} is not available here")
     keep = "--keep" in sys.argv  # leave the prepared directory behind (path printed) to re-run single tests by hand

@@ -30,6 +30,9 @@ def demangle(names):
 
 
 def main() -> None:
+    if "-h" in sys.argv or "--help" in sys.argv:
+        print(__doc__)
+        return
     if not os.path.isfile(LIB):
         raise SystemExit(f"{LIB} is not built: python -c 'import __graft_entry__ as g; g.build()'")
     res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True, check=True).stdout
