@@ -2,9 +2,11 @@
 """Run the REFERENCE's own unit tests against THIS package (launcher-side parity check).
 
 Needs /root/reference (build container only).  Nothing from the reference is copied into the repo: the selected test
-files are copied to a temporary directory, a meta-path finder aliases ``torchx.X`` to ``torchx_b200.X``, imports of
-out-of-scope names (Workspace, mounts, trackers, AWS resources, test fixtures) are stubbed, and pytest runs there.
-Failures that remain are listed; the known ones are out-of-scope features or tests that patch reference-internal names.
+files (with the data files next to them) are copied to a temporary directory, a meta-path finder aliases ``torchx.X`` to
+``torchx_b200.X``, the few imports of things this package does not have (the reference's test fixtures module, the AWS
+resource table, the worker-side tracker backends) are stubbed, plugin fixtures are renamed to this package's namespace
+(``torchx_b200_plugins``, ``torchx_b200.*`` entry-point groups), and pytest runs there, one process per file.
+Failures that remain are listed; they need cloud pieces (AWS table, a kubernetes scheduler, the booth example app).
 
     python tools/run_reference_tests.py            # prints one line per file: passed / failed
 """
