@@ -14,7 +14,6 @@ from __future__ import annotations
 import os
 import warnings
 from contextlib import contextmanager
-from datetime import timedelta
 from typing import Any, Iterator, Optional
 
 import torch

@@ -9,7 +9,6 @@ from __future__ import annotations
 
 import json
 import logging
-import sys
 import time
 import traceback
 from dataclasses import asdict, dataclass

@@ -43,14 +43,13 @@ import sys
 import threading
 import time
 from dataclasses import asdict, dataclass, field
-from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
+from typing import Any, Callable, Dict, List, Mapping, Optional, Tuple
 
 from torchx_b200.schedulers.api import DescribeAppResponse, ListAppResponse, Stream, filter_regex, split_lines_iterator
 from torchx_b200.schedulers.local_scheduler import (
     COMBINED_LOG,
     ENV_CUDA_VISIBLE_DEVICES,
     KILL_GRACE_S,
-    NA,
     STDERR_LOG,
     STDOUT_LOG,
     CWDImageProvider,
@@ -62,7 +61,6 @@ from torchx_b200.schedulers.local_scheduler import (
     PopenRequest,
     ReplicaParam,
     _LocalAppDef,
-    _LocalReplica,
 )
 from torchx_b200.schedulers.ids import make_unique
 from torchx_b200.specs.api import NONE, AppDef, AppDryRunInfo, AppState, CfgVal, Role, is_terminal, runopts

@@ -27,12 +27,11 @@ import pprint
 import shutil
 import signal
 import subprocess
-import sys
 import tempfile
 import threading
 import time
 import warnings
-from dataclasses import asdict, dataclass, field
+from dataclasses import asdict, dataclass
 from datetime import datetime
 from types import FrameType
 from typing import Any, BinaryIO, Callable, Dict, Iterable, List, Mapping, Optional, TextIO, Tuple

@@ -8,7 +8,7 @@ import io
 import os
 import threading
 import time
-from typing import BinaryIO, Dict, List, Optional, Sequence
+from typing import BinaryIO, Dict, Optional, Sequence
 
 
 class Tee:

@@ -18,10 +18,10 @@ import pathlib
 import re
 import shutil
 import string
-from dataclasses import asdict, dataclass, field, fields
+from dataclasses import asdict, dataclass, field
 from datetime import datetime
 from enum import Enum
-from typing import Any, Callable, Dict, Generic, Iterator, List, Mapping, NamedTuple, Optional, Tuple, Type, TypeVar, Union
+from typing import Any, Callable, Dict, Generic, Iterator, List, Mapping, NamedTuple, Optional, Tuple, TypeVar, Union
 
 from torchx_b200.util.types import to_dict
 

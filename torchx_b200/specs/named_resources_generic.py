@@ -1,7 +1,7 @@
-"""Generic t-shirt-size resources (reference torchx/specs/named_resources_generic.py:47-60; the AWS instance table and
-the fractional-resource machinery are cloud-only and out of scope).  ``dist.ddp -h gpu.xlarge`` resolves here; on
+"""Generic t-shirt-size resources (reference torchx/specs/named_resources_generic.py:47-60; the AWS instance table is cloud-only and out of scope;
+fractional variants come from ``plugins.register.named_resource(fractionals=...)``).  ``dist.ddp -h gpu.xlarge`` resolves here; on
 ``local_cuda`` the ``gpu`` count of the chosen resource caps how many devices a replica may claim."""
-from typing import Callable, Dict, Mapping
+from typing import Callable, Mapping
 
 from .api import Resource
 

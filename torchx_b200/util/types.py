@@ -6,7 +6,6 @@ literals must parse to the same Python values so `torchx run ... dist.ddp -j 1x8
 from __future__ import annotations
 
 import inspect
-import re
 import typing
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union, get_args, get_origin
 
